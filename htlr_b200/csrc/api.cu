@@ -1,0 +1,838 @@
+// C ABI of the CUDA sampler (include/htlr_cuda.h): handle life-cycle, the per-thin-step launch
+// sequence (eager or one captured CUDA graph per trajectory length), result fetch, parity hooks and
+// the NCCL plumbing for row-sharded X. No compute happens on the host and there is no CPU fallback.
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstddef>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/htlr_cuda.h"
+#include "common.cuh"
+#include "launch.h"
+
+using namespace htlr;
+
+namespace {
+
+thread_local std::string g_err;
+
+struct CudaFail {
+  int code;
+  std::string msg;
+};
+
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      throw CudaFail{HTLR_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)};             \
+  } while (0)
+#define NC(call)                                                                                   \
+  do {                                                                                             \
+    ncclResult_t r_ = (call);                                                                      \
+    if (r_ != ncclSuccess)                                                                         \
+      throw CudaFail{HTLR_E_NCCL, std::string(#call) + ": " + ncclGetErrorString(r_)};             \
+  } while (0)
+#define FAIL(code, text) throw CudaFail{code, text}
+
+int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+struct EventPair {
+  cudaEvent_t a, b;
+  int kind;  // 0 sweep, 1 step total, 2 sigma
+};
+
+}  // namespace
+
+struct htlr_handle {
+  htlr_cfg cfg{};
+  Geom g{};
+  Bufs b{};
+  cudaStream_t st = nullptr;
+  std::string err;
+  int iters_done = 0;  // outer iterations enqueued so far
+  std::vector<void*> allocs;
+  std::map<int, cudaGraphExec_t> graphs;
+  ncclComm_t comm = nullptr;
+  bool sharded = false;
+  bool profiling = false;
+  std::vector<EventPair> ev_pool;
+  size_t ev_used = 0;
+  htlr_profile prof{};
+  int64_t launches = 0;
+  int kernels_per_step_cache = 0;
+  // device scratch for the hooks
+  double *t_lv = nullptr, *t_R = nullptr, *t_pred = nullptr, *t_coef = nullptr, *t_g = nullptr, *t_vd = nullptr,
+         *t_momt = nullptr, *t_scalar = nullptr, *t_lvsave = nullptr;
+  int *t_idx = nullptr, *t_cnt = nullptr;
+  Ctl* t_ctlsave = nullptr;
+  // inject device buffers (addresses are baked into captured graphs)
+  double *inj[4] = {nullptr, nullptr, nullptr, nullptr};
+  int64_t inj_cap[4] = {0, 0, 0, 0};
+  unsigned long long cols_base = 0;  // Ctl::cols_swept at the last profile reset
+
+  template <class T>
+  T* dalloc(size_t count, bool zero = true) {
+    void* p = nullptr;
+    size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    CU(cudaMalloc(&p, bytes));
+    allocs.push_back(p);
+    if (zero) CU(cudaMemsetAsync(p, 0, bytes, st));
+    return static_cast<T*>(p);
+  }
+  int* ctl_int(size_t off) { return reinterpret_cast<int*>(reinterpret_cast<char*>(b.ctl) + off); }
+  double* ctl_dbl(size_t off) { return reinterpret_cast<double*>(reinterpret_cast<char*>(b.ctl) + off); }
+};
+
+namespace {
+
+void drop_graphs(htlr_handle* h) {
+  for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
+  h->graphs.clear();
+}
+
+int pick_L(const htlr_cfg& c, int i_mc) {
+  // Fit::Traject, gibbs.cpp:394-408
+  return (i_mc < c.iters_h) ? c.leap_L_h : c.leap_L;
+}
+
+// ---- profiling events --------------------------------------------------------------------------------
+void prof_drain(htlr_handle* h) {
+  if (!h->ev_used) return;
+  CU(cudaStreamSynchronize(h->st));
+  for (size_t i = 0; i < h->ev_used; ++i) {
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, h->ev_pool[i].a, h->ev_pool[i].b));
+    if (h->ev_pool[i].kind == 0) { h->prof.sweep_ms += ms; h->prof.sweep_launches += 1; }
+    else if (h->ev_pool[i].kind == 1) h->prof.total_ms += ms;
+    else h->prof.sigma_ms += ms;
+  }
+  h->ev_used = 0;
+}
+struct ProfScope {
+  htlr_handle* h;
+  EventPair* ep = nullptr;
+  ProfScope(htlr_handle* hh, int kind) : h(hh) {
+    if (!h->profiling) return;
+    if (h->ev_used == h->ev_pool.size()) {
+      if (h->ev_pool.size() >= 16384) prof_drain(h);
+      else {
+        EventPair p{};
+        CU(cudaEventCreate(&p.a));
+        CU(cudaEventCreate(&p.b));
+        h->ev_pool.push_back(p);
+      }
+    }
+    ep = &h->ev_pool[h->ev_used++];
+    ep->kind = kind;
+    CU(cudaEventRecord(ep->a, h->st));
+  }
+  ~ProfScope() {
+    if (ep) cudaEventRecord(ep->b, h->st);
+  }
+};
+
+// ---- one thin-step -------------------------------------------------------------------------------------
+// Order of Fit::StartSampling's loop body, gibbs.cpp:62-98.
+int enqueue_step(htlr_handle* h, int L, bool until_energy_only = false) {
+  const Geom& g = h->g;
+  const Bufs& b = h->b;
+  cudaStream_t st = h->st;
+  int nk = 0;
+  int* d_u = h->ctl_int(offsetof(Ctl, u));
+  double* gtarget = (g.g_rt == 1 && !h->sharded) ? b.g : b.gpart;
+  ProfScope whole(h, 1);
+  auto gradient = [&](int s) {
+    {
+      ProfScope ps(h, 0);
+      launch_grad_sweep(g, b, b.iup, d_u, b.R, gtarget, st);
+      ++nk;
+    }
+    if (h->sharded) {
+      launch_gsum(g, b, d_u, b.g, st);
+      ++nk;
+      NC(ncclAllReduce(b.g, b.g, (size_t)g.nvar * g.K + 1, ncclDouble, ncclSum, h->comm, st));
+    }
+    launch_post(g, b, s, L, h->sharded ? 1 : 0, st);
+    ++nk;
+  };
+  launch_select(g, b, st); ++nk;
+  launch_begin(g, b, st); ++nk;
+  {
+    ProfScope ps(h, 0);
+    launch_lv_sweep(g, b, 0, nullptr, nullptr, nullptr, st);
+    ++nk;
+  }
+  launch_softmax(g, b, 0, nullptr, nullptr, nullptr, nullptr, nullptr, st); ++nk;
+  gradient(0);
+  for (int t = 1; t <= L; ++t) {
+    {
+      ProfScope ps(h, 0);
+      launch_lv_sweep(g, b, 1, nullptr, nullptr, nullptr, st);
+      ++nk;
+    }
+    launch_softmax(g, b, 1, nullptr, nullptr, nullptr, nullptr, nullptr, st); ++nk;
+    gradient(t);
+  }
+  launch_energy(g, b, h->sharded ? 1 : 0, st); ++nk;
+  if (until_energy_only) return nk;
+  launch_commit(g, b, st); ++nk;
+  {
+    ProfScope ps(h, 2);
+    if (h->cfg.ptype == HTLR_PRIOR_T) {
+      launch_sigma(g, b, st); ++nk;
+      if (h->cfg.eta > 1e-10) { launch_logw(g, b, st); ++nk; }
+    } else {
+      launch_sigma_ars(g, b, st); ++nk;
+    }
+  }
+  launch_record(g, b, st); ++nk;
+  CU(cudaGetLastError());
+  return nk;
+}
+
+cudaGraphExec_t get_graph(htlr_handle* h, int L) {
+  auto it = h->graphs.find(L);
+  if (it != h->graphs.end()) return it->second;
+  cudaGraph_t graph;
+  CU(cudaStreamBeginCapture(h->st, cudaStreamCaptureModeThreadLocal));
+  int nk = 0;
+  try {
+    nk = enqueue_step(h, L);
+  } catch (...) {
+    cudaGraph_t junk = nullptr;
+    cudaStreamEndCapture(h->st, &junk);
+    if (junk) cudaGraphDestroy(junk);
+    throw;
+  }
+  CU(cudaStreamEndCapture(h->st, &graph));
+  cudaGraphExec_t exec;
+  CU(cudaGraphInstantiate(&exec, graph, 0));
+  CU(cudaGraphDestroy(graph));
+  h->graphs[L] = exec;
+  h->kernels_per_step_cache = nk;
+  return exec;
+}
+
+int kernels_per_step(const htlr_handle* h, int L) {
+  int per_grad = h->sharded ? 3 : 2;
+  int n = 2 + 2 + per_grad + L * (2 + per_grad) + 1 + 1 + 1 + 1;
+  if (h->cfg.ptype == HTLR_PRIOR_T && h->cfg.eta > 1e-10) n += 1;
+  return n;
+}
+
+void check_device_error(htlr_handle* h) {
+  Ctl c;
+  CU(cudaMemcpy(&c, h->b.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost));
+  if (c.err == kErrNone) return;
+  // clear so that the handle stays usable for inspection
+  int zero = 0;
+  CU(cudaMemcpy(h->ctl_int(offsetof(Ctl, err)), &zero, sizeof(int), cudaMemcpyHostToDevice));
+  switch (c.err) {
+    case kErrInjectNormals: FAIL(HTLR_E_SAMPLER, "injected normals exhausted");
+    case kErrInjectUniforms: FAIL(HTLR_E_SAMPLER, "injected uniforms exhausted");
+    case kErrInjectGammas: FAIL(HTLR_E_SAMPLER, "injected gammas exhausted");
+    case kErrInjectArs: FAIL(HTLR_E_SAMPLER, "injected ARS uniforms exhausted");
+    case kErrArs:
+      switch (c.err_detail) {
+        case 1: FAIL(HTLR_E_SAMPLER, "Error in adaptive rejection sampling:\nthe first tangent point doesn't have positive probability.\n");
+        case 2: FAIL(HTLR_E_SAMPLER, "Error in Rejection Sampling:\n'max_nhull' is set too small, or your log-PDF is NOT concave.\n");
+        case 3: FAIL(HTLR_E_SAMPLER, "Error: in C function 'sample_elin':\nthe exp linear function integrates to NAN/INFINITY\n");
+        default: FAIL(HTLR_E_SAMPLER, "adaptive rejection sampling did not terminate");
+      }
+    default: FAIL(HTLR_E_SAMPLER, "unknown device error " + std::to_string(c.err));
+  }
+}
+
+void upload_inject(htlr_handle* h, const htlr_inject* inj) {
+  const void* src[4] = {inj ? inj->normals : nullptr, inj ? inj->uniforms : nullptr, inj ? inj->gammas : nullptr,
+                        inj ? inj->ars_uniforms : nullptr};
+  int64_t cnt[4] = {inj ? inj->n_normals : 0, inj ? inj->n_uniforms : 0, inj ? inj->n_gammas : 0,
+                    inj ? inj->n_ars_blocks * (int64_t)h->cfg.ars_inject_width : 0};
+  for (int q = 0; q < 4; ++q) {
+    if (!src[q]) cnt[q] = 0;
+    if (cnt[q] > h->inj_cap[q]) {
+      CU(cudaStreamSynchronize(h->st));
+      drop_graphs(h);
+      if (h->inj[q]) CU(cudaFree(h->inj[q]));
+      int64_t cap = std::max<int64_t>(cnt[q], 1024);
+      CU(cudaMalloc((void**)&h->inj[q], cap * sizeof(double)));
+      h->inj_cap[q] = cap;
+    }
+    if (cnt[q]) CU(cudaMemcpyAsync(h->inj[q], src[q], cnt[q] * sizeof(double), cudaMemcpyHostToDevice, h->st));
+  }
+  h->b.inj_norm = h->inj[0];
+  h->b.inj_unif = h->inj[1];
+  h->b.inj_gam = h->inj[2];
+  h->b.inj_ars = h->inj[3];
+  // cursors restart, sizes updated: cur_norm, cur_unif, cur_gam, n_norm, n_unif, n_gam, n_ars_blocks
+  long long hdr[7] = {0, 0, 0, cnt[0], cnt[1], cnt[2], (inj && inj->ars_uniforms) ? inj->n_ars_blocks : 0};
+  CU(cudaMemcpyAsync(reinterpret_cast<char*>(h->b.ctl) + offsetof(Ctl, cur_norm), hdr, sizeof(hdr),
+                     cudaMemcpyHostToDevice, h->st));
+  long long zero = 0;
+  CU(cudaMemcpyAsync(reinterpret_cast<char*>(h->b.ctl) + offsetof(Ctl, step_in_call), &zero, sizeof(zero),
+                     cudaMemcpyHostToDevice, h->st));
+  CU(cudaStreamSynchronize(h->st));  // hdr / zero are stack variables
+}
+
+void do_create(const htlr_cfg* cfg, const double* X, int64_t ldx, const double* ymat, const int64_t* ybase,
+               const double* deltas0, const double* sigmasbt0, htlr_handle* h) {
+  if (!cfg || cfg->struct_size != sizeof(htlr_cfg)) FAIL(HTLR_E_ARG, "htlr_cfg.struct_size mismatch");
+  if (cfg->abi_version != HTLR_CUDA_ABI_VERSION) FAIL(HTLR_E_ARG, "htlr_cfg.abi_version mismatch");
+  const htlr_cfg& c = *cfg;
+  if (c.p < 1 || c.K < 1 || c.n < 1) FAIL(HTLR_E_ARG, "p, K, n must be positive");
+  if (c.K > kMaxK) FAIL(HTLR_E_ARG, "K > 16 classes-1 is not supported by this build");
+  if (c.ptype < 0 || c.ptype > 2) FAIL(HTLR_E_ARG, "Unsupported prior type");
+  if (!(c.iters_rmc > 0 && c.iters_h >= 0 && c.thin > 0 && c.leap_L > 0 && c.leap_L_h > 0))
+    FAIL(HTLR_E_ARG, "iters_rmc > 0, iters_h >= 0, thin > 0, leap_L > 0, leap_L_h > 0 required");
+  if (!(c.alpha > 0) || !(c.eta >= 0)) FAIL(HTLR_E_ARG, "alpha > 0 and eta >= 0 required");
+  if (!X || !ymat || !ybase || !deltas0 || !sigmasbt0) FAIL(HTLR_E_ARG, "null input array");
+  if (ldx < c.n) FAIL(HTLR_E_ARG, "ldx < n");
+  if (c.rng_mode != HTLR_RNG_DEVICE && c.rng_mode != HTLR_RNG_INJECT) FAIL(HTLR_E_ARG, "bad rng_mode");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    FAIL(HTLR_E_CUDA, "no CUDA device visible: this library has no CPU fallback");
+  if (c.device < 0 || c.device >= ndev) FAIL(HTLR_E_ARG, "device ordinal out of range");
+  CU(cudaSetDevice(c.device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, c.device));
+  if (prop.major != 10) FAIL(HTLR_E_CUDA, std::string("built for sm_100a only; device is ") + prop.name);
+
+  h->cfg = c;
+  h->sharded = c.nccl_comm != nullptr;
+  h->comm = static_cast<ncclComm_t>(c.nccl_comm);
+  CU(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+
+  const int n = c.n, K = c.K, nvar = c.p + 1;
+  Geom& g = h->g;
+  g.n = n; g.nvar = nvar; g.K = K;
+  g.n_s = (int)round_up(n, 16);
+  g.sm_count = prop.multiProcessorCount;
+  g.lv_rt = (n + 511) / 512;
+  g.lv_cs = (int)std::max<int64_t>(1, std::min<int64_t>((4 * g.sm_count + g.lv_rt - 1) / g.lv_rt, 1024));
+  g.g_tr = (int)std::min<int64_t>(g.n_s, K <= 4 ? 2048 : std::max(256, (8192 / K) / 64 * 64));
+  g.g_rt = (n + g.g_tr - 1) / g.g_tr;
+  g.g_gx = std::max(1, (4 * g.sm_count + g.g_rt - 1) / g.g_rt);
+  g.e_grid = std::max(1, std::min((nvar + 255) / 256, 2 * g.sm_count));
+
+  Bufs& b = h->b;
+  // ---- data
+  if (c.x_on_device) {
+    if (ldx % 2) FAIL(HTLR_E_ARG, "device-resident X needs an even leading dimension");
+    g.ld = ldx;
+    b.X = X;
+  } else {
+    g.ld = round_up(n, 16);
+    double* dX = h->dalloc<double>((size_t)g.ld * nvar, g.ld != n);
+    CU(cudaMemcpy2DAsync(dX, g.ld * sizeof(double), X, ldx * sizeof(double), (size_t)n * sizeof(double), nvar,
+                         cudaMemcpyHostToDevice, h->st));
+    b.X = dX;
+  }
+  std::vector<int64_t> yb_host(n);
+  if (c.x_on_device) CU(cudaMemcpy(yb_host.data(), ybase, n * sizeof(int64_t), cudaMemcpyDeviceToHost));
+  else std::memcpy(yb_host.data(), ybase, n * sizeof(int64_t));
+  std::vector<int> yb32(n);
+  for (int i = 0; i < n; ++i) {
+    if (yb_host[i] < 0 || yb_host[i] > K) FAIL(HTLR_E_ARG, "ybase out of range [0, C)");
+    yb32[i] = (int)yb_host[i];
+  }
+  int* d_yb = h->dalloc<int>(n);
+  CU(cudaMemcpyAsync(d_yb, yb32.data(), n * sizeof(int), cudaMemcpyHostToDevice, h->st));
+  b.ybase = d_yb;
+  double* d_ymat = h->dalloc<double>((size_t)g.n_s * K);
+  CU(cudaMemcpy2DAsync(d_ymat, g.n_s * sizeof(double), ymat, (size_t)n * sizeof(double), (size_t)n * sizeof(double),
+                       K, c.x_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->st));
+  b.ymat = d_ymat;
+  double* d_ddn = h->dalloc<double>(nvar);
+  b.ddn = d_ddn;
+
+  // ---- state
+  b.deltas = h->dalloc<double>((size_t)nvar * K);
+  b.sigmasbt = h->dalloc<double>(nvar);
+  b.var_deltas = h->dalloc<double>(nvar);
+  CU(cudaMemcpyAsync(b.deltas, deltas0, (size_t)nvar * K * sizeof(double), cudaMemcpyHostToDevice, h->st));
+  CU(cudaMemcpyAsync(b.sigmasbt, sigmasbt0, (size_t)nvar * sizeof(double), cudaMemcpyHostToDevice, h->st));
+  const size_t nk = (size_t)g.n_s * K;
+  b.lv = h->dalloc<double>(nk);
+  b.lv_old = h->dalloc<double>(nk);
+  b.lv_fix = h->dalloc<double>(nk);
+  b.R = h->dalloc<double>(nk);
+  b.iup = h->dalloc<int>(nvar);
+  b.ifix = h->dalloc<int>(nvar);
+  b.flags = h->dalloc<unsigned char>(nvar);
+  b.dc = h->dalloc<double>((size_t)nvar * K);
+  b.momt = h->dalloc<double>((size_t)nvar * K);
+  b.stepc = h->dalloc<double>(nvar);
+  b.sigc = h->dalloc<double>(nvar);
+  b.vdc = h->dalloc<double>(nvar);
+  b.g = h->dalloc<double>((size_t)nvar * K + 1);
+  b.gpart = h->dalloc<double>((size_t)g.g_rt * nvar * K);
+  b.lvpart = h->dalloc<double>((size_t)g.lv_cs * K * g.n_s);
+  b.red = h->dalloc<Red4>((size_t)std::max(std::max(g.e_grid, (n + 255) / 256), 1));
+  b.ctl = h->dalloc<Ctl>(1);
+
+  // ---- history
+  const int H = c.iters_rmc + 1 + (c.keep_warmup_hist ? c.iters_h : 0);
+  b.mcdeltas = h->dalloc<double>((size_t)nvar * K * H);
+  b.mcsigmasbt = h->dalloc<double>((size_t)nvar * H);
+  b.mcvardeltas = h->dalloc<double>((size_t)nvar * H);
+  b.mclogw = h->dalloc<double>(H);
+  b.mcloglike = h->dalloc<double>(H);
+  b.mcuvar = h->dalloc<double>(H);
+  b.mchmcrej = h->dalloc<double>(H);
+  b.stats = h->dalloc<Red4>(c.iters_h + c.iters_rmc);
+
+  // ---- control block
+  Ctl ctl;
+  std::memset(&ctl, 0, sizeof(ctl));
+  ctl.nvar = nvar; ctl.K = K; ctl.C = K + 1; ctl.n = n; ctl.p = c.p;
+  ctl.iters_h = c.iters_h; ctl.iters_rmc = c.iters_rmc; ctl.thin = c.thin;
+  ctl.keep_warmup_hist = c.keep_warmup_hist ? 1 : 0;
+  ctl.ptype = c.ptype; ctl.rng_mode = c.rng_mode;
+  ctl.alpha = c.alpha; ctl.s = c.s; ctl.eta = c.eta; ctl.leap_step = c.leap_step;
+  ctl.sgmsq_cut = c.hmc_sgmcut > 0 ? c.hmc_sgmcut * c.hmc_sgmcut : c.hmc_sgmcut;  // gibbs.cpp:14
+  ctl.seed = c.seed;
+  ctl.logw = c.s;
+  ctl.init_all = 1;
+  ctl.ars_width = c.ars_inject_width;
+  CU(cudaMemcpyAsync(b.ctl, &ctl, sizeof(ctl), cudaMemcpyHostToDevice, h->st));
+  CU(cudaStreamSynchronize(h->st));  // ctl / yb32 are host temporaries
+
+  // ---- Fit::Fit tail + Fit::Initialize (gibbs.cpp:15, 519-530)
+  launch_colsumsq(g, b.X, d_ddn, h->st);
+  if (h->sharded) NC(ncclAllReduce(d_ddn, d_ddn, nvar, ncclDouble, ncclSum, h->comm, h->st));
+  launch_select(g, b, h->st);
+  int* d_u = h->ctl_int(offsetof(Ctl, u));
+  launch_lv_sweep(g, b, 2, b.iup, d_u, b.deltas, h->st);
+  double* d_ll = h->ctl_dbl(offsetof(Ctl, loglike));
+  launch_softmax(g, b, 2, d_u, b.lv, b.R, nullptr, d_ll, h->st);
+  if (h->sharded) NC(ncclAllReduce(d_ll, d_ll, 1, ncclDouble, ncclSum, h->comm, h->st));
+  launch_vardeltas_all(g, b, h->st);
+  h->launches += 5;
+  CU(cudaMemcpyAsync(b.mcdeltas, b.deltas, (size_t)nvar * K * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+  CU(cudaMemcpyAsync(b.mcsigmasbt, b.sigmasbt, (size_t)nvar * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+  CU(cudaMemcpyAsync(b.mcvardeltas, b.var_deltas, (size_t)nvar * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+  CU(cudaMemcpyAsync(b.mcloglike, d_ll, sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+  CU(cudaMemcpyAsync(b.mclogw, h->ctl_dbl(offsetof(Ctl, logw)), sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+  int zero = 0;
+  CU(cudaMemcpyAsync(h->ctl_int(offsetof(Ctl, init_all)), &zero, sizeof(int), cudaMemcpyHostToDevice, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  CU(cudaGetLastError());
+}
+
+void ensure_scratch(htlr_handle* h) {
+  if (h->t_lv) return;
+  const Geom& g = h->g;
+  const size_t nk = (size_t)g.n_s * g.K;
+  h->t_lv = h->dalloc<double>(nk);
+  h->t_R = h->dalloc<double>(nk);
+  h->t_lvsave = h->dalloc<double>(nk);
+  h->t_pred = h->dalloc<double>((size_t)g.n * (g.K + 1));
+  h->t_coef = h->dalloc<double>((size_t)g.nvar * g.K);
+  h->t_momt = h->dalloc<double>((size_t)g.nvar * g.K);
+  h->t_g = h->dalloc<double>((size_t)g.g_rt * g.nvar * g.K + 1);
+  h->t_vd = h->dalloc<double>(g.nvar);
+  h->t_scalar = h->dalloc<double>(4);
+  h->t_idx = h->dalloc<int>(g.nvar);
+  h->t_cnt = h->dalloc<int>(1);
+  h->t_ctlsave = h->dalloc<Ctl>(1);
+}
+
+// [k][i] stride n_s  ->  n x C column-major with a zero first column
+void lv_to_host(htlr_handle* h, const double* d_lv, double* out) {
+  const Geom& g = h->g;
+  std::memset(out, 0, sizeof(double) * g.n);
+  CU(cudaMemcpy2D(out + g.n, (size_t)g.n * sizeof(double), d_lv, (size_t)g.n_s * sizeof(double),
+                  (size_t)g.n * sizeof(double), g.K, cudaMemcpyDeviceToHost));
+}
+
+template <class F>
+int guarded(htlr_handle* h, F&& f) {
+  try {
+    f();
+    return HTLR_OK;
+  } catch (const CudaFail& e) {
+    if (h) h->err = e.msg; else g_err = e.msg;
+    g_err = e.msg;
+    return e.code;
+  } catch (const std::exception& e) {
+    if (h) h->err = e.what();
+    g_err = e.what();
+    return HTLR_E_STATE;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t htlr_cuda_abi_version(void) { return HTLR_CUDA_ABI_VERSION; }
+
+const char* htlr_cuda_last_error(const htlr_handle* h) { return h ? h->err.c_str() : g_err.c_str(); }
+
+int htlr_cuda_create(const htlr_cfg* cfg, const double* X, int64_t ldx, const double* ymat, const int64_t* ybase,
+                     const double* deltas0, const double* sigmasbt0, htlr_handle** out) {
+  if (!out) { g_err = "null out pointer"; return HTLR_E_ARG; }
+  *out = nullptr;
+  htlr_handle* h = new htlr_handle();
+  int rc = guarded(nullptr, [&] { do_create(cfg, X, ldx, ymat, ybase, deltas0, sigmasbt0, h); });
+  if (rc != HTLR_OK) {
+    htlr_cuda_destroy(h);
+    return rc;
+  }
+  *out = h;
+  return HTLR_OK;
+}
+
+void htlr_cuda_destroy(htlr_handle* h) {
+  if (!h) return;
+  if (h->st) cudaStreamSynchronize(h->st);
+  drop_graphs(h);
+  for (auto& p : h->ev_pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+  for (void* p : h->allocs) cudaFree(p);
+  for (int q = 0; q < 4; ++q) if (h->inj[q]) cudaFree(h->inj[q]);
+  if (h->st) cudaStreamDestroy(h->st);
+  delete h;
+}
+
+int32_t htlr_cuda_hist_len(const htlr_handle* h) {
+  return h->cfg.iters_rmc + 1 + (h->cfg.keep_warmup_hist ? h->cfg.iters_h : 0);
+}
+
+static void enqueue_iters(htlr_handle* h, int32_t n_iters) {
+  const htlr_cfg& c = h->cfg;
+  if (n_iters < 0 || h->iters_done + n_iters > c.iters_h + c.iters_rmc)
+    FAIL(HTLR_E_STATE, "run past the configured number of iterations");
+  CU(cudaSetDevice(c.device));
+  const bool graph = c.use_graph && !h->profiling;
+  for (int it = 0; it < n_iters; ++it) {
+    const int L = pick_L(c, h->iters_done);
+    for (int t = 0; t < c.thin; ++t) {
+      if (graph) {
+        cudaGraphExec_t ge = get_graph(h, L);
+        CU(cudaGraphLaunch(ge, h->st));
+        h->launches += kernels_per_step(h, L);
+      } else {
+        h->launches += enqueue_step(h, L);
+      }
+    }
+    h->iters_done += 1;
+  }
+}
+
+int htlr_cuda_run_async(htlr_handle* h, int32_t n_iters) {
+  if (!h) return HTLR_E_ARG;
+  return guarded(h, [&] {
+    if (h->cfg.rng_mode == HTLR_RNG_INJECT) FAIL(HTLR_E_STATE, "run_async needs the device RNG");
+    enqueue_iters(h, n_iters);
+  });
+}
+
+int htlr_cuda_sync(htlr_handle* h) {
+  if (!h) return HTLR_E_ARG;
+  return guarded(h, [&] {
+    CU(cudaStreamSynchronize(h->st));
+    check_device_error(h);
+  });
+}
+
+int htlr_cuda_run(htlr_handle* h, int32_t n_iters, const htlr_inject* inject, htlr_iter_stats* stats) {
+  if (!h) return HTLR_E_ARG;
+  return guarded(h, [&] {
+    CU(cudaSetDevice(h->cfg.device));
+    if (h->cfg.rng_mode == HTLR_RNG_INJECT) {
+      if (!inject) FAIL(HTLR_E_ARG, "rng_mode INJECT needs an htlr_inject");
+      upload_inject(h, inject);
+    }
+    const int first = h->iters_done;
+    enqueue_iters(h, n_iters);
+    CU(cudaStreamSynchronize(h->st));
+    check_device_error(h);
+    if (stats && n_iters > 0) {
+      static_assert(sizeof(htlr_iter_stats) == sizeof(Red4), "stats layout");
+      CU(cudaMemcpy(stats, h->b.stats + first, sizeof(Red4) * n_iters, cudaMemcpyDeviceToHost));
+    }
+  });
+}
+
+int htlr_cuda_fetch(htlr_handle* h, double* mcdeltas, double* mcsigmasbt, double* mcvardeltas, double* mclogw,
+                    double* mcloglike, double* mcuvar, double* mchmcrej, double* ddnloglike) {
+  if (!h) return HTLR_E_ARG;
+  return guarded(h, [&] {
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaStreamSynchronize(h->st));
+    const size_t H = htlr_cuda_hist_len(h), nvar = h->g.nvar, K = h->g.K;
+    auto get = [&](double* dst, const double* src, size_t cnt) {
+      if (dst) CU(cudaMemcpy(dst, src, cnt * sizeof(double), cudaMemcpyDeviceToHost));
+    };
+    get(mcdeltas, h->b.mcdeltas, nvar * K * H);
+    get(mcsigmasbt, h->b.mcsigmasbt, nvar * H);
+    get(mcvardeltas, h->b.mcvardeltas, nvar * H);
+    get(mclogw, h->b.mclogw, H);
+    get(mcloglike, h->b.mcloglike, H);
+    get(mcuvar, h->b.mcuvar, H);
+    get(mchmcrej, h->b.mchmcrej, H);
+    get(ddnloglike, h->b.ddn, nvar);
+  });
+}
+
+int htlr_cuda_get_state(htlr_handle* h, double* lv, double* deltas, double* sigmasbt, double* var_deltas,
+                        double* loglike, double* logw) {
+  if (!h) return HTLR_E_ARG;
+  return guarded(h, [&] {
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaStreamSynchronize(h->st));
+    const size_t nvar = h->g.nvar, K = h->g.K;
+    if (lv) lv_to_host(h, h->b.lv, lv);
+    if (deltas) CU(cudaMemcpy(deltas, h->b.deltas, nvar * K * sizeof(double), cudaMemcpyDeviceToHost));
+    if (sigmasbt) CU(cudaMemcpy(sigmasbt, h->b.sigmasbt, nvar * sizeof(double), cudaMemcpyDeviceToHost));
+    if (var_deltas) CU(cudaMemcpy(var_deltas, h->b.var_deltas, nvar * sizeof(double), cudaMemcpyDeviceToHost));
+    Ctl c;
+    CU(cudaMemcpy(&c, h->b.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost));
+    if (loglike) *loglike = c.loglike;
+    if (logw) *logw = c.logw;
+  });
+}
+
+int htlr_cuda_eval(htlr_handle* h, const int32_t* iup, int32_t u, const double* deltas, double* lv, double* pred,
+                   double* loglike, double* grad) {
+  if (!h) return HTLR_E_ARG;
+  return guarded(h, [&] {
+    if (!iup || !deltas || u < 0 || u > h->g.nvar) FAIL(HTLR_E_ARG, "bad restricted set");
+    if (h->sharded) FAIL(HTLR_E_STATE, "eval hook is single-GPU only");
+    CU(cudaSetDevice(h->cfg.device));
+    ensure_scratch(h);
+    const Geom& g = h->g;
+    const size_t nvar = g.nvar, K = g.K;
+    for (int q = 0; q < u; ++q)
+      if (iup[q] < 0 || iup[q] >= g.nvar) FAIL(HTLR_E_ARG, "restricted-set index out of range");
+    CU(cudaMemcpyAsync(h->t_idx, iup, sizeof(int) * u, cudaMemcpyHostToDevice, h->st));
+    CU(cudaMemcpyAsync(h->t_cnt, &u, sizeof(int), cudaMemcpyHostToDevice, h->st));
+    CU(cudaMemcpyAsync(h->t_coef, deltas, sizeof(double) * nvar * K, cudaMemcpyHostToDevice, h->st));
+    launch_lv_sweep(g, h->b, 2, h->t_idx, h->t_cnt, h->t_coef, h->st);
+    launch_softmax(g, h->b, 2, h->t_cnt, h->t_lv, h->t_R, h->t_pred, h->t_scalar, h->st);
+    launch_grad_sweep(g, h->b, h->t_idx, h->t_cnt, h->t_R, h->t_g, h->st);
+    h->launches += 3;
+    CU(cudaStreamSynchronize(h->st));
+    CU(cudaGetLastError());
+    if (lv) lv_to_host(h, h->t_lv, lv);
+    if (pred) CU(cudaMemcpy(pred, h->t_pred, sizeof(double) * g.n * (K + 1), cudaMemcpyDeviceToHost));
+    if (loglike) CU(cudaMemcpy(loglike, h->t_scalar, sizeof(double), cudaMemcpyDeviceToHost));
+    if (grad) {
+      std::vector<double> part((size_t)g.g_rt * nvar * K);
+      CU(cudaMemcpy(part.data(), h->t_g, part.size() * sizeof(double), cudaMemcpyDeviceToHost));
+      // compact [r*K + k] (summed over row tiles in tile order) -> u x K column-major
+      for (int q = 0; q < u; ++q)
+        for (size_t k = 0; k < K; ++k) {
+          double a = 0;
+          for (int rt = 0; rt < g.g_rt; ++rt) a += part[(size_t)rt * nvar * K + (size_t)q * K + k];
+          grad[k * u + q] = a;
+        }
+    }
+  });
+}
+
+int htlr_cuda_trajectory(htlr_handle* h, const double* momt, int32_t L, double* deltas_out, double* momt_out,
+                         double* lv_out, double* loglike_out, double* var_deltas_out, double* nenergy_old,
+                         double* nenergy_new, int32_t* nuvar) {
+  if (!h) return HTLR_E_ARG;
+  return guarded(h, [&] {
+    if (!momt || L < 1) FAIL(HTLR_E_ARG, "bad trajectory arguments");
+    CU(cudaSetDevice(h->cfg.device));
+    ensure_scratch(h);
+    const Geom& g = h->g;
+    const size_t nvar = g.nvar, K = g.K, nk = (size_t)g.n_s * K;
+    CU(cudaStreamSynchronize(h->st));
+    // snapshot what a proposal touches: control block and lv (deltas / var_deltas change only on commit)
+    CU(cudaMemcpyAsync(h->t_ctlsave, h->b.ctl, sizeof(Ctl), cudaMemcpyDeviceToDevice, h->st));
+    CU(cudaMemcpyAsync(h->t_lvsave, h->b.lv, nk * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+    CU(cudaMemcpyAsync(h->t_momt, momt, nvar * K * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    int dev_rng = 0;
+    CU(cudaMemcpyAsync(h->ctl_int(offsetof(Ctl, rng_mode)), &dev_rng, sizeof(int), cudaMemcpyHostToDevice, h->st));
+    const bool prof = h->profiling;
+    h->profiling = false;
+    h->b.user_momt = h->t_momt;
+    try {
+      h->launches += enqueue_step(h, L, /*until_energy_only=*/true);
+    } catch (...) {
+      h->b.user_momt = nullptr;
+      h->profiling = prof;
+      throw;
+    }
+    h->b.user_momt = nullptr;
+    h->profiling = prof;
+    // proposal in full layout
+    CU(cudaMemcpyAsync(h->t_coef, h->b.deltas, nvar * K * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+    CU(cudaMemsetAsync(h->t_momt, 0, nvar * K * sizeof(double), h->st));
+    CU(cudaMemcpyAsync(h->t_vd, h->b.var_deltas, nvar * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+    launch_scatter_proposal(g, h->b, h->t_coef, h->t_momt, h->t_vd, h->st);
+    h->launches += 1;
+    CU(cudaStreamSynchronize(h->st));
+    CU(cudaGetLastError());
+    Ctl c;
+    CU(cudaMemcpy(&c, h->b.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost));
+    if (deltas_out) CU(cudaMemcpy(deltas_out, h->t_coef, nvar * K * sizeof(double), cudaMemcpyDeviceToHost));
+    if (momt_out) CU(cudaMemcpy(momt_out, h->t_momt, nvar * K * sizeof(double), cudaMemcpyDeviceToHost));
+    if (var_deltas_out) CU(cudaMemcpy(var_deltas_out, h->t_vd, nvar * sizeof(double), cudaMemcpyDeviceToHost));
+    if (lv_out) lv_to_host(h, h->b.lv, lv_out);
+    if (loglike_out) *loglike_out = c.loglike_new;
+    if (nenergy_old) *nenergy_old = c.nenergy_old;
+    if (nenergy_new) *nenergy_new = c.nenergy_new;
+    if (nuvar) *nuvar = c.u;
+    // restore
+    CU(cudaMemcpyAsync(h->b.ctl, h->t_ctlsave, sizeof(Ctl), cudaMemcpyDeviceToDevice, h->st));
+    CU(cudaMemcpyAsync(h->b.lv, h->t_lvsave, nk * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+    CU(cudaStreamSynchronize(h->st));
+  });
+}
+
+int htlr_cuda_ars(int32_t device, int32_t kind, int32_t m, const double* var_deltas, double K, double alpha,
+                  double log_aw, const double* uniforms, int32_t width, uint64_t seed, uint64_t step, double* x_out,
+                  int32_t* n_unif, int32_t* n_eval, int32_t* status) {
+  return guarded(nullptr, [&] {
+    if (m < 1 || !var_deltas || !x_out) FAIL(HTLR_E_ARG, "bad ARS arguments");
+    if (kind != HTLR_PRIOR_GHS && kind != HTLR_PRIOR_NEG) FAIL(HTLR_E_ARG, "kind must be ghs or neg");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) FAIL(HTLR_E_CUDA, "no CUDA device visible");
+    CU(cudaSetDevice(device));
+    double *d_v = nullptr, *d_u = nullptr, *d_x = nullptr;
+    int *d_nu = nullptr, *d_ne = nullptr, *d_st = nullptr;
+    CU(cudaMalloc((void**)&d_v, sizeof(double) * m));
+    CU(cudaMalloc((void**)&d_x, sizeof(double) * m));
+    CU(cudaMalloc((void**)&d_nu, sizeof(int) * m));
+    CU(cudaMalloc((void**)&d_ne, sizeof(int) * m));
+    CU(cudaMalloc((void**)&d_st, sizeof(int) * m));
+    CU(cudaMemcpy(d_v, var_deltas, sizeof(double) * m, cudaMemcpyHostToDevice));
+    if (uniforms) {
+      CU(cudaMalloc((void**)&d_u, sizeof(double) * (size_t)m * width));
+      CU(cudaMemcpy(d_u, uniforms, sizeof(double) * (size_t)m * width, cudaMemcpyHostToDevice));
+    }
+    launch_ars_standalone(kind, m, d_v, K, alpha, log_aw, d_u, width, seed, step, d_x, d_nu, d_ne, d_st, 0);
+    CU(cudaDeviceSynchronize());
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(x_out, d_x, sizeof(double) * m, cudaMemcpyDeviceToHost));
+    if (n_unif) CU(cudaMemcpy(n_unif, d_nu, sizeof(int) * m, cudaMemcpyDeviceToHost));
+    if (n_eval) CU(cudaMemcpy(n_eval, d_ne, sizeof(int) * m, cudaMemcpyDeviceToHost));
+    if (status) CU(cudaMemcpy(status, d_st, sizeof(int) * m, cudaMemcpyDeviceToHost));
+    cudaFree(d_v); cudaFree(d_x); cudaFree(d_nu); cudaFree(d_ne); cudaFree(d_st);
+    if (d_u) cudaFree(d_u);
+  });
+}
+
+int htlr_cuda_rng_dump(int32_t device, uint64_t seed, uint32_t purpose, uint64_t step, int32_t n_a, int32_t n_b,
+                       int32_t kind, double shape, double* out) {
+  return guarded(nullptr, [&] {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) FAIL(HTLR_E_CUDA, "no CUDA device visible");
+    CU(cudaSetDevice(device));
+    double* d = nullptr;
+    const size_t tot = (size_t)n_a * n_b;
+    CU(cudaMalloc((void**)&d, sizeof(double) * tot));
+    launch_rng_dump(seed, purpose, step, n_a, n_b, kind, shape, d, 0);
+    CU(cudaDeviceSynchronize());
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(out, d, sizeof(double) * tot, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+  });
+}
+
+void* htlr_cuda_stream(htlr_handle* h) { return h ? (void*)h->st : nullptr; }
+
+int htlr_cuda_profile_enable(htlr_handle* h, int32_t on) {
+  if (!h) return HTLR_E_ARG;
+  return guarded(h, [&] {
+    CU(cudaSetDevice(h->cfg.device));
+    prof_drain(h);
+    h->profiling = on != 0;
+  });
+}
+
+int htlr_cuda_profile_get(htlr_handle* h, htlr_profile* out, int32_t reset) {
+  if (!h || !out) return HTLR_E_ARG;
+  return guarded(h, [&] {
+    CU(cudaSetDevice(h->cfg.device));
+    prof_drain(h);
+    CU(cudaStreamSynchronize(h->st));
+    Ctl c;
+    CU(cudaMemcpy(&c, h->b.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost));
+    h->prof.kernel_launches = h->launches;
+    h->prof.sweep_bytes = 8.0 * h->g.n * (double)(c.cols_swept - h->cols_base);
+    *out = h->prof;
+    if (reset) {
+      h->prof = htlr_profile{};
+      h->cols_base = c.cols_swept;
+    }
+  });
+}
+
+int64_t htlr_cuda_launch_count(const htlr_handle* h) { return h ? h->launches : 0; }
+
+int htlr_cuda_fit(const htlr_cfg* cfg, const double* X, int64_t ldx, const double* ymat, const int64_t* ybase,
+                  const double* deltas0, const double* sigmasbt0, const htlr_inject* inject, htlr_tick_fn tick,
+                  void* user, double* mcdeltas, double* mcsigmasbt, double* mcvardeltas, double* mclogw,
+                  double* mcloglike, double* mcuvar, double* mchmcrej, double* ddnloglike, char* errbuf,
+                  size_t errbuf_len) {
+  htlr_handle* h = nullptr;
+  auto fail = [&](int rc, const char* msg) {
+    if (errbuf && errbuf_len) snprintf(errbuf, errbuf_len, "%s", msg);
+    if (h) htlr_cuda_destroy(h);
+    return rc;
+  };
+  int rc = htlr_cuda_create(cfg, X, ldx, ymat, ybase, deltas0, sigmasbt0, &h);
+  if (rc) return fail(rc, htlr_cuda_last_error(nullptr));
+  const int total = cfg->iters_h + cfg->iters_rmc;
+  if (cfg->rng_mode == HTLR_RNG_INJECT) {
+    // injected streams are positional: run everything in one call
+    std::vector<htlr_iter_stats> st(total);
+    rc = htlr_cuda_run(h, total, inject, st.data());
+    if (rc) return fail(rc, htlr_cuda_last_error(h));
+    if (tick && tick(user, total, st.data(), total)) return fail(HTLR_E_STATE, "interrupted");
+  } else {
+    std::vector<htlr_iter_stats> st(256);
+    for (int done = 0; done < total;) {
+      // the reference polls for interrupts when i_mc % 256 == 0 (gibbs.cpp:124)
+      const int chunk = std::min(256, total - done);
+      rc = htlr_cuda_run(h, chunk, nullptr, st.data());
+      if (rc) return fail(rc, htlr_cuda_last_error(h));
+      done += chunk;
+      if (tick && tick(user, done, st.data(), chunk)) return fail(HTLR_E_STATE, "interrupted");
+    }
+  }
+  rc = htlr_cuda_fetch(h, mcdeltas, mcsigmasbt, mcvardeltas, mclogw, mcloglike, mcuvar, mchmcrej, ddnloglike);
+  if (rc) return fail(rc, htlr_cuda_last_error(h));
+  htlr_cuda_destroy(h);
+  return HTLR_OK;
+}
+
+int htlr_cuda_nccl_unique_id(void* id128) {
+  return guarded(nullptr, [&] {
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    ncclUniqueId id;
+    NC(ncclGetUniqueId(&id));
+    std::memcpy(id128, &id, sizeof(id));
+  });
+}
+
+int htlr_cuda_nccl_init(const void* id128, int32_t rank, int32_t world, int32_t device, void** comm) {
+  return guarded(nullptr, [&] {
+    CU(cudaSetDevice(device));
+    ncclUniqueId id;
+    std::memcpy(&id, id128, sizeof(id));
+    ncclComm_t c;
+    NC(ncclCommInitRank(&c, world, id, rank));
+    *comm = c;
+  });
+}
+
+void htlr_cuda_nccl_destroy(void* comm) {
+  if (comm) ncclCommDestroy(static_cast<ncclComm_t>(comm));
+}
+
+}  // extern "C"

@@ -1,0 +1,94 @@
+// Shared device-side definitions for the HTLR sampler kernels.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace htlr {
+
+constexpr int kMaxK = 16;  // classes - 1 supported by the generic kernels (templated fast paths for K <= 4)
+
+// Error codes stored in Ctl::err (sticky, first one wins).
+enum DevErr : int {
+  kErrNone = 0,
+  kErrInjectNormals = 1,
+  kErrInjectUniforms = 2,
+  kErrInjectGammas = 3,
+  kErrInjectArs = 4,
+  kErrArs = 16,  // + ArsStatus in err_detail
+};
+
+// Device-resident control block: everything that varies from thin-step to thin-step lives here so a
+// single captured CUDA graph can be replayed for every iteration with no host round trip.
+struct Ctl {
+  // static configuration
+  int nvar, K, C, n, p;
+  int iters_h, iters_rmc, thin, keep_warmup_hist, ptype, rng_mode;
+  double alpha, s, eta, leap_step, sgmsq_cut;
+  unsigned long long seed;
+  // progress
+  int i_mc, i_thin;
+  unsigned long long step;       // global thin-step index (Philox key)
+  long long step_in_call;        // thin-steps since the current run() call (inject block index)
+  // restricted set
+  int u, nfix, init_all;
+  // chain scalars
+  double logw, loglike, loglike_new, loglike_old;
+  double nenergy_old, nenergy_new;
+  int accept;
+  double uvar_acc, rej_acc;
+  // inject cursors and sizes
+  long long cur_norm, cur_unif, cur_gam, n_norm, n_unif, n_gam, n_ars_blocks;
+  int ars_width;
+  // errors
+  int err, err_detail;
+  // X columns swept so far (lv + gradient sweeps), for the roofline arithmetic
+  unsigned long long cols_swept;
+  // scratch counters for "last block finishes" reductions
+  unsigned int ticket[8];
+};
+
+struct Red4 {
+  double a, b, c, d;
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Sum over the block in a fixed order (lanes by xor-tree, then warps left to right). Result valid in
+// every thread. `sm` must hold 32 doubles.
+__device__ __forceinline__ double block_sum(double v, double* sm) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) sm[w] = v;
+  __syncthreads();
+  double t = 0;
+  for (int i = 0; i < nw; ++i) t += sm[i];
+  return t;
+}
+
+__device__ __forceinline__ void set_err(Ctl* ctl, int code, int detail) {
+  if (atomicCAS(&ctl->err, 0, code) == 0) ctl->err_detail = detail;
+}
+
+// Grid-wide "last block done" election. Returns true in exactly one block (all its threads), after the
+// writes of every other block are visible.
+__device__ __forceinline__ bool last_block(unsigned int* ticket, unsigned int nblocks) {
+  __shared__ unsigned int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int t = atomicAdd(ticket, 1u);
+    s_last = (t == nblocks - 1);
+    if (s_last) *ticket = 0;  // re-arm for the next launch
+  }
+  __syncthreads();
+  if (s_last) __threadfence();
+  return s_last != 0;
+}
+
+}  // namespace htlr

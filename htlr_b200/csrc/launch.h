@@ -1,0 +1,92 @@
+// Host-callable launch wrappers (defined in the kernel translation units, used by api.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "common.cuh"
+
+namespace htlr {
+
+// Geometry of the sweep kernels, fixed at create time (grids never depend on the restricted-set size,
+// which only the device knows; surplus blocks exit immediately).
+struct Geom {
+  int n, nvar, K;
+  int64_t ld;       // leading dimension of X on the device (doubles), even
+  int n_s;          // row stride of n-length arrays (lv, R, ymat), even
+  // lv sweep: 256 threads x 2 rows per block
+  int lv_rt;        // row tiles
+  int lv_cs;        // max column splits (partial-sum slots)
+  // gradient sweep: 8 warps per block, one column per warp at a time
+  int g_tr;         // rows per tile
+  int g_rt;         // row tiles
+  int g_gx;         // blocks per row tile
+  // elementwise kernels over the restricted set
+  int e_grid;
+  int sm_count;
+};
+
+struct Bufs {
+  // data
+  const double* X;
+  const double* ymat;   // [k][i], stride n_s
+  const int* ybase;
+  const double* ddn;    // colsum(X^2)/4
+  // chain state
+  double *deltas, *sigmasbt, *var_deltas;   // nvar x K col-major, nvar, nvar
+  double *lv, *lv_old, *lv_fix, *R;         // [k][i], stride n_s (class columns 1..K; class 0 is 0)
+  // restricted set + compact per-feature work arrays (index r = position in iup)
+  int *iup, *ifix;
+  double *dc, *momt, *stepc, *sigc, *vdc;   // u x K, u x K, u, u, u
+  double* g;            // gradient, u x K (+1 trailing slot for the local log-likelihood when sharded)
+  double* gpart;        // [g_rt][nvar*K] partials when g_rt > 1
+  double* lvpart;       // [lv_cs][K][n_s]
+  Red4* red;            // per-block partial sums
+  Ctl* ctl;
+  // history
+  double *mcdeltas, *mcsigmasbt, *mcvardeltas, *mclogw, *mcloglike, *mcuvar, *mchmcrej;
+  htlr::Red4* stats;    // per outer iteration: loglike, logw, uvar, rej
+  // inject
+  const double *inj_norm, *inj_unif, *inj_gam, *inj_ars;
+  // optional user momenta for htlr_cuda_trajectory (nvar x K col-major) or null
+  const double* user_momt;
+  unsigned char* flags; // nvar scratch for the selection scan
+};
+
+void launch_colsumsq(const Geom& g, const double* X, double* ddn, cudaStream_t st);
+void launch_select(const Geom& g, const Bufs& b, cudaStream_t st);
+void launch_begin(const Geom& g, const Bufs& b, cudaStream_t st);
+// mode 0: detach sweep (iup/compact coefficients if u <= nvar/2 else ifix/global deltas)
+// mode 1: trajectory sweep over iup with compact coefficients
+// mode 2: explicit index list + global coefficient matrix (eval hook, Initialize)
+void launch_lv_sweep(const Geom& g, const Bufs& b, int mode, const int* idx, const int* cnt,
+                     const double* coef_global, cudaStream_t st);
+// what 0: detach finish (lv_old = lv, lv_fix, R from current lv)
+// what 1: trajectory softmax (lv = lv_fix + sum of partials, R, log-likelihood -> ctl.loglike_new)
+// what 2: like 1 but lv_fix taken as zero and also writes pred (n x C col-major) if non-null
+void launch_softmax(const Geom& g, const Bufs& b, int what, const int* cnt, double* lv_out, double* R_out,
+                    double* pred_out, double* loglike_out, cudaStream_t st);
+void launch_grad_sweep(const Geom& g, const Bufs& b, const int* idx, const int* cnt, const double* R,
+                       double* gout, cudaStream_t st);
+// sums row-tile partials into g (only needed before an all-reduce; k_post does it itself otherwise)
+void launch_gsum(const Geom& g, const Bufs& b, const int* cnt, double* gout, cudaStream_t st);
+void launch_post(const Geom& g, const Bufs& b, int s, int L, int g_is_summed, cudaStream_t st);
+void launch_energy(const Geom& g, const Bufs& b, int g_has_loglike, cudaStream_t st);
+void launch_commit(const Geom& g, const Bufs& b, cudaStream_t st);
+void launch_record(const Geom& g, const Bufs& b, cudaStream_t st);
+void launch_vardeltas_all(const Geom& g, const Bufs& b, cudaStream_t st);
+void launch_scatter_proposal(const Geom& g, const Bufs& b, double* deltas_out, double* momt_out,
+                             double* vd_out, cudaStream_t st);
+
+// sigma_kernels.cu (compiled with --fmad=false)
+void launch_sigma(const Geom& g, const Bufs& b, cudaStream_t st);      // t prior: gamma draws
+void launch_sigma_ars(const Geom& g, const Bufs& b, cudaStream_t st);  // ghs / neg: warp-per-feature ARS
+void launch_logw(const Geom& g, const Bufs& b, cudaStream_t st);
+void launch_ars_standalone(int kind, int m, const double* vard, double K, double alpha, double log_aw,
+                           const double* uniforms, int width, unsigned long long seed,
+                           unsigned long long step, double* x_out, int* n_unif, int* n_eval, int* status,
+                           cudaStream_t st);
+void launch_rng_dump(unsigned long long seed, unsigned int purpose, unsigned long long step, int n_a, int n_b,
+                     int kind, double shape, double* out, cudaStream_t st);
+
+}  // namespace htlr

@@ -1,0 +1,610 @@
+// HMC / restricted-Gibbs kernels of the two-sweep path (the reference's own structure: one X sweep for
+// the linear predictor and one for the gradient per leapfrog step). All FP64.
+//
+// Reference functions replaced (paths relative to the reference root):
+//   k_colsumsq     DDNloglike_ = colsum(X^2)/4                         src/gibbs.cpp:15
+//   k_select       Fit::WhichUpdate                                    src/gibbs.cpp:156-170
+//   k_begin        GenMomt, UpdateStepSizes, CacheOldValues(deltas),   src/gibbs.cpp:441-460, 477-481, 483-491,
+//                  CompNegEnergy (old)                                 432-437
+//   k_lv_sweep     triple loops of UpdatePredProb / DetachFixlv        src/gibbs.cpp:179-188, 203-227
+//   k_softmax      find_normlv + exp, UpdateLogLike, residual of       src/utils.cpp:10-26, gibbs.cpp:189-190,
+//                  UpdateDNlogLike (pred - ymat)                       254-261, 238
+//   k_grad_sweep   triple loop of UpdateDNlogLike                      src/gibbs.cpp:239-249
+//   k_post         UpdateDNlogPrior, UpdateDNlogPost, MoveMomt,        src/gibbs.cpp:267-283, 467-471, 291-297
+//                  UpdateMomtAndDeltas
+//   k_energy       UpdateVarDeltas, CompNegEnergy (new), IsFault,      src/gibbs.cpp:425-437, 503-516, 89-95
+//                  Metropolis test
+//   k_commit       keep proposal / RestoreOldValues                    src/gibbs.cpp:493-501
+//   k_record       trace recording                                     src/gibbs.cpp:100-114
+//
+// Layout: X column-major n x nvar with even leading dimension (each feature one contiguous column);
+// n-length arrays [k][i] with stride n_s; compact per-feature arrays indexed by position r in iup,
+// [r*K + k].
+#include <cstdio>
+
+#include "common.cuh"
+#include "launch.h"
+#include "rng.cuh"
+
+namespace htlr {
+
+#define DISPATCH_K(KV, ...)                          \
+  switch (KV) {                                      \
+    case 1: { constexpr int KT = 1; __VA_ARGS__; } break; \
+    case 2: { constexpr int KT = 2; __VA_ARGS__; } break; \
+    case 3: { constexpr int KT = 3; __VA_ARGS__; } break; \
+    case 4: { constexpr int KT = 4; __VA_ARGS__; } break; \
+    default: { constexpr int KT = 0; __VA_ARGS__; } break; \
+  }
+
+template <int KT>
+struct KDim {
+  static constexpr int kMax = KT > 0 ? KT : kMaxK;
+};
+
+__device__ __forceinline__ double2 ldg2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
+
+// ------------------------------------------------------------------------------------------------
+__global__ void k_colsumsq(Geom g, const double* __restrict__ X, double* __restrict__ ddn) {
+  const int lane = threadIdx.x & 31;
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (int j = w; j < g.nvar; j += nw) {
+    const double* x = X + (int64_t)j * g.ld;
+    double a = 0;
+    for (int i = lane; i < g.n; i += 32) a += x[i] * x[i];
+    a = warp_sum(a);
+    if (lane == 0) ddn[j] = a / 4;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Ordered compaction of the restricted set by ONE block: thread t owns the contiguous chunk
+// [t*chunk, (t+1)*chunk) so ascending order falls out of an exclusive scan over per-thread counts.
+__global__ void __launch_bounds__(1024) k_select(Geom g, Bufs b) {
+  Ctl* ctl = b.ctl;
+  __shared__ int s_w[32];
+  __shared__ int s_total;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int nvar = g.nvar;
+  const double cut = ctl->init_all ? -1.0 : ctl->sgmsq_cut;
+  for (int j = tid; j < nvar; j += 1024) b.flags[j] = b.sigmasbt[j] > cut;
+  __syncthreads();
+  const int chunk = (nvar + 1023) / 1024;
+  const int j0 = min(nvar, tid * chunk), j1 = min(nvar, j0 + chunk);
+  int c = 0;
+  for (int j = j0; j < j1; ++j) c += b.flags[j];
+  int inc = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) s_w[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    int v = s_w[lane], iv = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, iv, o);
+      if (lane >= o) iv += t;
+    }
+    s_w[lane] = iv - v;  // exclusive warp offsets
+    if (lane == 31) s_total = iv;
+  }
+  __syncthreads();
+  int pu = s_w[w] + inc - c;
+  int pf = j0 - pu;
+  for (int j = j0; j < j1; ++j) {
+    if (b.flags[j]) b.iup[pu++] = j; else b.ifix[pf++] = j;
+  }
+  if (tid == 0) {
+    const int u = s_total;
+    ctl->u = u;
+    ctl->nfix = nvar - u;
+    if (!ctl->init_all) {
+      ctl->uvar_acc += u;
+      // Traject's choice of logw (gibbs.cpp:394-408); L itself is chosen by the host
+      ctl->logw = (ctl->i_mc < ctl->iters_h / 2.0) ? -10.0 : ctl->s;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_begin(Geom g, Bufs b) {
+  Ctl* ctl = b.ctl;
+  __shared__ double sm[32];
+  const int u = ctl->u, K = g.K, nvar = g.nvar;
+  const KeyedRng rng{ctl->seed};
+  double pa = 0, pb = 0;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < u; r += gridDim.x * blockDim.x) {
+    const int j = b.iup[r];
+    const double sig = b.sigmasbt[j];
+    b.sigc[r] = sig;
+    b.stepc[r] = ctl->leap_step / sqrt(b.ddn[j] + (double)K / sig / (double)ctl->C);
+    pa += b.var_deltas[j] / sig;
+    for (int k = 0; k < K; ++k) {
+      b.dc[(int64_t)r * K + k] = b.deltas[(int64_t)k * nvar + j];
+      double m;
+      if (b.user_momt) {
+        m = b.user_momt[(int64_t)k * nvar + j];
+      } else if (ctl->rng_mode == 1) {
+        long long at = ctl->cur_norm + (long long)r * K + k;
+        if (at >= ctl->n_norm) { set_err(ctl, kErrInjectNormals, 0); m = 0; }
+        else m = b.inj_norm[at];
+      } else {
+        m = rng.norm(kRngMomentum, ctl->step, (uint32_t)j, (uint32_t)k);
+      }
+      b.momt[(int64_t)r * K + k] = m;
+      pb += m * m;
+    }
+  }
+  pa = block_sum(pa, sm);
+  pb = block_sum(pb, sm);
+  if (threadIdx.x == 0) { b.red[blockIdx.x].a = pa; b.red[blockIdx.x].b = pb; }
+  if (last_block(&ctl->ticket[0], gridDim.x)) {
+    if (threadIdx.x == 0) {
+      double A = 0, B = 0;
+      for (unsigned i = 0; i < gridDim.x; ++i) { A += b.red[i].a; B += b.red[i].b; }
+      ctl->nenergy_old = ctl->loglike - A / 2 - B / 2;
+      ctl->loglike_old = ctl->loglike;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Which columns a sweep covers and how many partial-sum slots it fills. Shared by k_lv_sweep and
+// k_softmax so both agree without a host round trip.
+struct ColSet {
+  const int* idx;
+  int cnt;
+  const double* cg;  // global coefficient matrix (nvar x K col-major) or null for compact dc
+  int slots;
+};
+__device__ __forceinline__ ColSet resolve_cols(const Geom& g, const Bufs& b, int mode, const int* idx_in,
+                                               const int* cnt_in, const double* coef_global) {
+  const Ctl* ctl = b.ctl;
+  ColSet c;
+  if (mode == 0) {
+    if (ctl->u <= g.nvar / 2) { c.idx = b.iup; c.cnt = ctl->u; c.cg = nullptr; }
+    else { c.idx = b.ifix; c.cnt = ctl->nfix; c.cg = b.deltas; }
+  } else if (mode == 1) {
+    c.idx = b.iup; c.cnt = ctl->u; c.cg = nullptr;
+  } else {
+    c.idx = idx_in; c.cnt = *cnt_in; c.cg = coef_global;
+  }
+  int want = (c.cnt + 7) / 8;
+  c.slots = min(g.lv_cs, max(1, want));
+  return c;
+}
+
+// partial[cs][k][i] = sum over this block's share of the column set of X[i, j] * coef[j, k].
+// Thread = two consecutive rows (128-bit loads, 4 KB contiguous per block per column).
+template <int KT>
+__global__ void __launch_bounds__(256) k_lv_sweep(Geom g, Bufs b, int mode, const int* idx_in,
+                                                   const int* cnt_in, const double* coef_global) {
+  constexpr int KM = KDim<KT>::kMax;
+  const int K = KT > 0 ? KT : g.K;
+  const ColSet cs = resolve_cols(g, b, mode, idx_in, cnt_in, coef_global);
+  const int s = blockIdx.x;
+  if (s == 0 && blockIdx.y == 0 && threadIdx.x == 0) b.ctl->cols_swept += (unsigned long long)cs.cnt;
+  if (s >= cs.slots) return;
+  const int c0 = (int)((int64_t)s * cs.cnt / cs.slots), c1 = (int)((int64_t)(s + 1) * cs.cnt / cs.slots);
+  const int i = blockIdx.y * 512 + 2 * threadIdx.x;
+  if (i >= g.n) return;
+  const bool tail = (i + 1 >= g.n);
+  double a0[KM], a1[KM];
+#pragma unroll
+  for (int k = 0; k < KM; ++k) { a0[k] = 0; a1[k] = 0; }
+  const double* Xi = b.X + i;
+  const int nvar = g.nvar;
+  int r = c0;
+  for (; r + 4 <= c1; r += 4) {
+    int j[4];
+    double2 x[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) j[q] = __ldg(cs.idx + r + q);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) x[q] = ldg2(Xi + (int64_t)j[q] * g.ld);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+      for (int k = 0; k < KM; ++k) {
+        if (k < K) {
+          const double c = cs.cg ? __ldg(cs.cg + (int64_t)k * nvar + j[q]) : __ldg(b.dc + (int64_t)(r + q) * K + k);
+          a0[k] = fma(x[q].x, c, a0[k]);
+          a1[k] = fma(x[q].y, c, a1[k]);
+        }
+      }
+    }
+  }
+  for (; r < c1; ++r) {
+    const int j = __ldg(cs.idx + r);
+    const double2 x = ldg2(Xi + (int64_t)j * g.ld);
+#pragma unroll
+    for (int k = 0; k < KM; ++k) {
+      if (k < K) {
+        const double c = cs.cg ? __ldg(cs.cg + (int64_t)k * nvar + j) : __ldg(b.dc + (int64_t)r * K + k);
+        a0[k] = fma(x.x, c, a0[k]);
+        a1[k] = fma(x.y, c, a1[k]);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < KM; ++k) {
+    if (k < K) {
+      double* o = b.lvpart + ((int64_t)s * K + k) * g.n_s + i;
+      if (tail) o[0] = a0[k];
+      else *reinterpret_cast<double2*>(o) = make_double2(a0[k], a1[k]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int KT>
+__global__ void __launch_bounds__(256) k_softmax(Geom g, Bufs b, int what, const int* cnt_in, double* lv_out,
+                                                  double* R_out, double* pred_out, double* loglike_out) {
+  constexpr int KM = KDim<KT>::kMax;
+  const int K = KT > 0 ? KT : g.K;
+  Ctl* ctl = b.ctl;
+  __shared__ double sm[32];
+  const ColSet cs = resolve_cols(g, b, what == 0 ? 0 : (what == 1 ? 1 : 2), nullptr, cnt_in, nullptr);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double ll = 0;
+  if (i < g.n) {
+    double l[KM];
+#pragma unroll
+    for (int k = 0; k < KM; ++k) {
+      if (k < K) {
+        double sacc = 0;
+        for (int s = 0; s < cs.slots; ++s) sacc += b.lvpart[((int64_t)s * K + k) * g.n_s + i];
+        const int64_t e = (int64_t)k * g.n_s + i;
+        if (what == 0) {
+          const double cur = b.lv[e];
+          b.lv_old[e] = cur;
+          b.lv_fix[e] = (ctl->u <= g.nvar / 2) ? cur - sacc : sacc;
+          l[k] = cur;
+        } else if (what == 1) {
+          l[k] = b.lv_fix[e] + sacc;
+          b.lv[e] = l[k];
+        } else {
+          l[k] = sacc;
+          lv_out[e] = sacc;
+        }
+      }
+    }
+    // find_normlv (utils.cpp:10-26): max-shifted log-sum-exp over the C classes, class 0 has lv = 0
+    double m = 0.0;
+#pragma unroll
+    for (int k = 0; k < KM; ++k) if (k < K) m = fmax(m, l[k]);
+    double se = exp(0.0 - m);
+#pragma unroll
+    for (int k = 0; k < KM; ++k) if (k < K) se += exp(l[k] - m);
+    const double lse = log(se) + m;
+    const int yb = b.ybase[i];
+    if (yb == 0) ll = 0.0 - lse;
+    if (pred_out) pred_out[i] = exp(0.0 - lse);
+    double* R = what == 2 ? R_out : b.R;
+#pragma unroll
+    for (int k = 0; k < KM; ++k) {
+      if (k < K) {
+        const double nl = l[k] - lse;
+        const double pr = exp(nl);
+        if (yb == k + 1) ll = nl;
+        if (pred_out) pred_out[(int64_t)(k + 1) * g.n + i] = pr;
+        R[(int64_t)k * g.n_s + i] = pr - b.ymat[(int64_t)k * g.n_s + i];
+      }
+    }
+  }
+  if (what == 0) return;
+  ll = block_sum(ll, sm);
+  if (threadIdx.x == 0) b.red[blockIdx.x].c = ll;
+  if (last_block(&ctl->ticket[1], gridDim.x)) {
+    if (threadIdx.x == 0) {
+      double A = 0;
+      for (unsigned q = 0; q < gridDim.x; ++q) A += b.red[q].c;
+      if (what == 1) ctl->loglike_new = A; else *loglike_out = A;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// g[r, k] = sum_i X[i, idx[r]] * R[i, k]: one warp per column, residual tile staged in shared memory,
+// 128-bit column loads, lane-strided partial sums + xor-tree (deterministic).
+template <int KT>
+__global__ void __launch_bounds__(256) k_grad_sweep(Geom g, Bufs b, const int* idx, const int* cnt_in,
+                                                     const double* __restrict__ R, double* __restrict__ gout) {
+  constexpr int KM = KDim<KT>::kMax;
+  const int K = KT > 0 ? KT : g.K;
+  extern __shared__ double sR[];  // [K][g_tr]
+  const int cnt = *cnt_in;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) b.ctl->cols_swept += (unsigned long long)cnt;
+  const int rt = blockIdx.y, i0 = rt * g.g_tr;
+  const int rows = min(g.g_tr, g.n - i0);
+  for (int e = threadIdx.x; e < K * g.g_tr; e += blockDim.x) {
+    const int k = e / g.g_tr, ii = e - k * g.g_tr;
+    sR[e] = ii < rows ? R[(int64_t)k * g.n_s + i0 + ii] : 0.0;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int pairs = (rows + 1) >> 1;
+  double* out = gout + (int64_t)rt * g.nvar * K;
+  for (int r = blockIdx.x * 8 + warp; r < cnt; r += gridDim.x * 8) {
+    const int j = __ldg(idx + r);
+    const double* xc = b.X + (int64_t)j * g.ld + i0;
+    double acc[KM];
+#pragma unroll
+    for (int k = 0; k < KM; ++k) acc[k] = 0;
+    int m = lane;
+    for (; m + 96 < pairs; m += 128) {
+      double2 x[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) x[q] = ldg2(xc + 2 * (m + 32 * q));
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int mm = m + 32 * q;
+        if (2 * mm + 1 >= rows) x[q].y = 0;
+#pragma unroll
+        for (int k = 0; k < KM; ++k) {
+          if (k < K) {
+            const double2 rr = *reinterpret_cast<const double2*>(sR + k * g.g_tr + 2 * mm);
+            acc[k] = fma(x[q].x, rr.x, acc[k]);
+            acc[k] = fma(x[q].y, rr.y, acc[k]);
+          }
+        }
+      }
+    }
+    for (; m < pairs; m += 32) {
+      double2 x = ldg2(xc + 2 * m);
+      if (2 * m + 1 >= rows) x.y = 0;
+#pragma unroll
+      for (int k = 0; k < KM; ++k) {
+        if (k < K) {
+          const double2 rr = *reinterpret_cast<const double2*>(sR + k * g.g_tr + 2 * m);
+          acc[k] = fma(x.x, rr.x, acc[k]);
+          acc[k] = fma(x.y, rr.y, acc[k]);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < KM; ++k) {
+      if (k < K) {
+        const double v = warp_sum(acc[k]);
+        if (lane == 0) out[(int64_t)r * K + k] = v;
+      }
+    }
+  }
+}
+
+// Sum the row-tile partials (needed on its own only before an all-reduce).
+__global__ void k_gsum(Geom g, Bufs b, const int* cnt_in, double* gout) {
+  const int cnt = *cnt_in, K = g.K;
+  const int64_t total = (int64_t)cnt * K;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    double a = 0;
+    for (int rt = 0; rt < g.g_rt; ++rt) a += b.gpart[(int64_t)rt * g.nvar * K + e];
+    gout[e] = a;
+  }
+  // the local log-likelihood rides along in the trailing slot (row-sharded all-reduce)
+  if (blockIdx.x == 0 && threadIdx.x == 0) gout[(int64_t)g.nvar * K] = b.ctl->loglike_new;
+}
+
+// ------------------------------------------------------------------------------------------------
+// After gradient sweep s (0..L): DNlogprior, DNlogpost, then MoveMomt of step s (s >= 1) and
+// UpdateMomtAndDeltas of step s+1 (s < L) — both use the same DNlogpost, two separate half kicks as in
+// the reference. Products are kept un-fused so every element matches the CPU arithmetic.
+__global__ void __launch_bounds__(256) k_post(Geom g, Bufs b, int s, int L, int g_is_summed) {
+  const Ctl* ctl = b.ctl;
+  const int u = ctl->u, K = g.K;
+  const double Cd = (double)ctl->C;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < u; r += gridDim.x * blockDim.x) {
+    double* d = b.dc + (int64_t)r * K;
+    double* mo = b.momt + (int64_t)r * K;
+    const double sig = b.sigc[r], st = b.stepc[r], hs = st / 2;
+    double sd = d[0];
+    for (int k = 1; k < K; ++k) sd += d[k];
+    const double sdc = sd / Cd;
+    for (int k = 0; k < K; ++k) {
+      double gl;
+      if (g_is_summed || g.g_rt == 1) {
+        gl = b.g[(int64_t)r * K + k];
+      } else {
+        gl = 0;
+        for (int rt = 0; rt < g.g_rt; ++rt) gl += b.gpart[(int64_t)rt * g.nvar * K + (int64_t)r * K + k];
+      }
+      const double post = gl + (d[k] - sdc) / sig;
+      double m = mo[k];
+      const double kick = __dmul_rn(hs, post);
+      if (s >= 1) m = __dsub_rn(m, kick);
+      if (s < L) {
+        m = __dsub_rn(m, kick);
+        d[k] = __dadd_rn(d[k], __dmul_rn(st, m));
+      }
+      mo[k] = m;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_energy(Geom g, Bufs b, int g_has_loglike) {
+  Ctl* ctl = b.ctl;
+  __shared__ double sm[32];
+  const int u = ctl->u, K = g.K;
+  const double Cd = (double)ctl->C;
+  double pa = 0, pb = 0, fault = 0;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < u; r += gridDim.x * blockDim.x) {
+    const double* d = b.dc + (int64_t)r * K;
+    const double* mo = b.momt + (int64_t)r * K;
+    double sd = d[0], ss = __dmul_rn(d[0], d[0]);
+    if (fabs(d[0]) > 20) fault = 1;
+    pb += mo[0] * mo[0];
+    for (int k = 1; k < K; ++k) {
+      sd += d[k];
+      ss = __dadd_rn(ss, __dmul_rn(d[k], d[k]));
+      if (fabs(d[k]) > 20) fault = 1;
+      pb += mo[k] * mo[k];
+    }
+    const double vd = ss - __dmul_rn(sd, sd) / Cd;
+    b.vdc[r] = vd;
+    pa += vd / b.sigc[r];
+  }
+  pa = block_sum(pa, sm);
+  pb = block_sum(pb, sm);
+  fault = block_sum(fault, sm);
+  if (threadIdx.x == 0) { b.red[blockIdx.x].a = pa; b.red[blockIdx.x].b = pb; b.red[blockIdx.x].d = fault; }
+  if (last_block(&ctl->ticket[2], gridDim.x)) {
+    if (threadIdx.x == 0) {
+      double A = 0, B = 0, F = 0;
+      for (unsigned i = 0; i < gridDim.x; ++i) { A += b.red[i].a; B += b.red[i].b; F += b.red[i].d; }
+      if (g_has_loglike) ctl->loglike_new = b.g[(int64_t)g.nvar * K];
+      const double ne = ctl->loglike_new - A / 2 - B / 2;
+      ctl->nenergy_new = ne;
+      double uu;
+      if (ctl->rng_mode == 1) {
+        if (ctl->cur_unif >= ctl->n_unif) { set_err(ctl, kErrInjectUniforms, 0); uu = 0.5; }
+        else uu = b.inj_unif[ctl->cur_unif];
+      } else {
+        const KeyedRng rng{ctl->seed};
+        uu = rng.unif(kRngAccept, ctl->step, 0, 0);
+      }
+      // gibbs.cpp:90 — NaN energies fall through to "accept", exactly as in the reference
+      const bool reject = (log(uu) > (ne - ctl->nenergy_old)) || (F > 0);
+      ctl->accept = reject ? 0 : 1;
+      if (reject) ctl->rej_acc += 1;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_commit(Geom g, Bufs b) {
+  Ctl* ctl = b.ctl;
+  const int u = ctl->u, K = g.K, nvar = g.nvar;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  if (ctl->accept) {
+    for (int r = tid; r < u; r += nt) {
+      const int j = b.iup[r];
+      for (int k = 0; k < K; ++k) b.deltas[(int64_t)k * nvar + j] = b.dc[(int64_t)r * K + k];
+      b.var_deltas[j] = b.vdc[r];
+    }
+    if (tid == 0) ctl->loglike = ctl->loglike_new;
+  } else {
+    const int64_t tot = (int64_t)K * g.n_s;
+    for (int64_t e = tid; e < tot; e += nt) b.lv[e] = b.lv_old[e];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_record(Geom g, Bufs b) {
+  Ctl* ctl = b.ctl;
+  const int nvar = g.nvar, K = g.K;
+  const bool last_thin = (ctl->i_thin == ctl->thin - 1);
+  const int i_rmc = ctl->keep_warmup_hist ? (ctl->i_mc + 1) : (ctl->i_mc - ctl->iters_h + 1);
+  if (last_thin && i_rmc > 0) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    double* md = b.mcdeltas + (int64_t)i_rmc * nvar * K;
+    for (int64_t e = tid; e < (int64_t)nvar * K; e += nt) md[e] = b.deltas[e];
+    double* ms = b.mcsigmasbt + (int64_t)i_rmc * nvar;
+    double* mv = b.mcvardeltas + (int64_t)i_rmc * nvar;
+    for (int j = tid; j < nvar; j += nt) { ms[j] = b.sigmasbt[j]; mv[j] = b.var_deltas[j]; }
+  }
+  if (last_block(&ctl->ticket[3], gridDim.x)) {
+    if (threadIdx.x == 0) {
+      // advance inject cursors (reference consumption: u*K normals, 1 uniform, p gammas per thin-step)
+      ctl->cur_norm += (long long)ctl->u * K;
+      ctl->cur_unif += 1;
+      if (ctl->ptype == 0) ctl->cur_gam += ctl->p;
+      ctl->step += 1;
+      ctl->step_in_call += 1;
+      if (last_thin) {
+        const double uv = ctl->uvar_acc / ctl->thin, rj = ctl->rej_acc / ctl->thin;
+        if (i_rmc > 0) {
+          b.mclogw[i_rmc] = ctl->logw;
+          b.mcloglike[i_rmc] = ctl->loglike;
+          b.mcuvar[i_rmc] = uv;
+          b.mchmcrej[i_rmc] = rj;
+        }
+        Red4 st;
+        st.a = ctl->loglike; st.b = ctl->logw; st.c = uv; st.d = rj;
+        b.stats[ctl->i_mc] = st;
+        ctl->uvar_acc = 0;
+        ctl->rej_acc = 0;
+        ctl->i_thin = 0;
+        ctl->i_mc += 1;
+      } else {
+        ctl->i_thin += 1;
+      }
+    }
+  }
+}
+
+// UpdateDNlogPrior + UpdateVarDeltas over every feature (Initialize, gibbs.cpp:527-528)
+__global__ void k_vardeltas_all(Geom g, Bufs b) {
+  const int nvar = g.nvar, K = g.K;
+  const double Cd = (double)(K + 1);
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nvar; j += gridDim.x * blockDim.x) {
+    double sd = b.deltas[j], ss = __dmul_rn(sd, sd);
+    for (int k = 1; k < K; ++k) {
+      const double d = b.deltas[(int64_t)k * nvar + j];
+      sd += d;
+      ss = __dadd_rn(ss, __dmul_rn(d, d));
+    }
+    b.var_deltas[j] = ss - __dmul_rn(sd, sd) / Cd;
+  }
+}
+
+// Proposal in full (nvar-sized) layout for the trajectory test hook.
+__global__ void k_scatter_proposal(Geom g, Bufs b, double* deltas_out, double* momt_out, double* vd_out) {
+  const Ctl* ctl = b.ctl;
+  const int u = ctl->u, K = g.K, nvar = g.nvar;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < u; r += gridDim.x * blockDim.x) {
+    const int j = b.iup[r];
+    for (int k = 0; k < K; ++k) {
+      deltas_out[(int64_t)k * nvar + j] = b.dc[(int64_t)r * K + k];
+      momt_out[(int64_t)k * nvar + j] = b.momt[(int64_t)r * K + k];
+    }
+    vd_out[j] = b.vdc[r];
+  }
+}
+
+// ================================================================================================
+void launch_colsumsq(const Geom& g, const double* X, double* ddn, cudaStream_t st) {
+  k_colsumsq<<<g.sm_count * 4, 256, 0, st>>>(g, X, ddn);
+}
+void launch_select(const Geom& g, const Bufs& b, cudaStream_t st) { k_select<<<1, 1024, 0, st>>>(g, b); }
+void launch_begin(const Geom& g, const Bufs& b, cudaStream_t st) { k_begin<<<g.e_grid, 256, 0, st>>>(g, b); }
+
+void launch_lv_sweep(const Geom& g, const Bufs& b, int mode, const int* idx, const int* cnt,
+                     const double* coef_global, cudaStream_t st) {
+  dim3 grid(g.lv_cs, g.lv_rt);
+  DISPATCH_K(g.K, k_lv_sweep<KT><<<grid, 256, 0, st>>>(g, b, mode, idx, cnt, coef_global));
+}
+void launch_softmax(const Geom& g, const Bufs& b, int what, const int* cnt, double* lv_out, double* R_out,
+                    double* pred_out, double* loglike_out, cudaStream_t st) {
+  const int grid = (g.n + 255) / 256;
+  DISPATCH_K(g.K, k_softmax<KT><<<grid, 256, 0, st>>>(g, b, what, cnt, lv_out, R_out, pred_out, loglike_out));
+}
+void launch_grad_sweep(const Geom& g, const Bufs& b, const int* idx, const int* cnt, const double* R,
+                       double* gout, cudaStream_t st) {
+  dim3 grid(g.g_gx, g.g_rt);
+  const size_t smem = (size_t)g.K * g.g_tr * sizeof(double);
+  DISPATCH_K(g.K, k_grad_sweep<KT><<<grid, 256, smem, st>>>(g, b, idx, cnt, R, gout));
+}
+void launch_gsum(const Geom& g, const Bufs& b, const int* cnt, double* gout, cudaStream_t st) {
+  k_gsum<<<g.e_grid, 256, 0, st>>>(g, b, cnt, gout);
+}
+void launch_post(const Geom& g, const Bufs& b, int s, int L, int g_is_summed, cudaStream_t st) {
+  k_post<<<g.e_grid, 256, 0, st>>>(g, b, s, L, g_is_summed);
+}
+void launch_energy(const Geom& g, const Bufs& b, int g_has_loglike, cudaStream_t st) {
+  k_energy<<<g.e_grid, 256, 0, st>>>(g, b, g_has_loglike);
+}
+void launch_commit(const Geom& g, const Bufs& b, cudaStream_t st) { k_commit<<<g.e_grid, 256, 0, st>>>(g, b); }
+void launch_record(const Geom& g, const Bufs& b, cudaStream_t st) { k_record<<<g.e_grid, 256, 0, st>>>(g, b); }
+void launch_vardeltas_all(const Geom& g, const Bufs& b, cudaStream_t st) {
+  k_vardeltas_all<<<g.e_grid, 256, 0, st>>>(g, b);
+}
+void launch_scatter_proposal(const Geom& g, const Bufs& b, double* deltas_out, double* momt_out, double* vd_out,
+                             cudaStream_t st) {
+  k_scatter_proposal<<<g.e_grid, 256, 0, st>>>(g, b, deltas_out, momt_out, vd_out);
+}
+
+}  // namespace htlr

@@ -1,0 +1,199 @@
+// Per-feature variance ("sigmasbt") updates and the logw update. Compiled with --fmad=false so the
+// scalar arithmetic of the samplers rounds like the CPU reference's (no fused multiply-adds).
+//
+// Reference functions replaced:
+//   k_sigma (t prior)    Fit::UpdateSigmasT + spl_sgm_ig            src/gibbs.cpp:311-331, src/utils.cpp:29-33
+//   k_sigma (ghs / neg)  Fit::UpdateSigmasSgm/Ghs/Neg + ARS engine  src/gibbs.cpp:351-388, src/sampler.cpp:18-49,
+//                                                                   src/ars.cpp (see ars.cuh)
+//   k_logw               Fit::UpdateLogw + SamplerLogw              src/gibbs.cpp:333-348, src/sampler.cpp:57-72
+#include "ars.cuh"
+#include "common.cuh"
+#include "launch.h"
+#include "rng.cuh"
+
+namespace htlr {
+
+// t prior: one thread per feature. sigma^2_j = (alpha*e^logw + var_deltas_j)/2 / Gamma((alpha+K)/2, 1).
+__global__ void __launch_bounds__(256) k_sigma_t(Geom g, Bufs b) {
+  Ctl* ctl = b.ctl;
+  const int p = ctl->p;
+  const double shape = (ctl->alpha + ctl->K) / 2;
+  const double w = exp(ctl->logw);
+  const KeyedRng rng{ctl->seed};
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < p; q += gridDim.x * blockDim.x) {
+    const int j = q + 1;
+    double gm;
+    if (ctl->rng_mode == 1) {
+      const long long at = ctl->cur_gam + q;
+      if (at >= ctl->n_gam) { set_err(ctl, kErrInjectGammas, 0); gm = 1.0; }
+      else gm = b.inj_gam[at];
+    } else {
+      gm = rng.gamma(ctl->step, (uint32_t)j, shape);
+    }
+    b.sigmasbt[j] = (1.0 / gm * (ctl->alpha * w + b.var_deltas[j]) / 2.0);
+  }
+}
+
+// ghs / neg: one warp per feature, ARS on x = log sigma^2_j from x0 = log(var_deltas_j / K).
+__global__ void __launch_bounds__(256) k_sigma_ars(Geom g, Bufs b) {
+  Ctl* ctl = b.ctl;
+  const int p = ctl->p;
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const double log_aw = ctl->logw + log(ctl->alpha);
+  for (int q = warp; q < p; q += nwarps) {
+    const int j = q + 1;
+    SgmTarget tg{ctl->ptype, b.var_deltas[j], (double)ctl->K, ctl->alpha, log_aw};
+    const double x0 = log(tg.v / tg.K);
+    double x = 0;
+    int status;
+    if (ctl->rng_mode == 1) {
+      const long long blk = ctl->step_in_call * (long long)(p + 1) + q;
+      ArsArrayUniforms un{b.inj_ars + blk * ctl->ars_width, blk < ctl->n_ars_blocks ? ctl->ars_width : 0, 0};
+      ArsWarp<SgmTarget, ArsArrayUniforms> ars(tg, un);
+      status = ars.sample(x0, x);
+    } else {
+      ArsKeyedUniforms un{ctl->seed, ctl->step, kRngArs, (uint32_t)j, 0u};
+      ArsWarp<SgmTarget, ArsKeyedUniforms> ars(tg, un);
+      status = ars.sample(x0, x);
+    }
+    if (status != kArsOk) {
+      if (lane == 0) set_err(ctl, status == kArsNoUniforms ? kErrInjectArs : kErrArs, status);
+      x = NAN;
+    }
+    if (lane == 0) b.sigmasbt[j] = exp(x);
+  }
+}
+
+// logw | var_deltas (t prior, eta > 0): block-collective target, every warp runs the engine redundantly.
+struct LogwEval {
+  const double* vd;  // var_deltas[1..p]
+  int p;
+  double K, nu, s, eta;
+  double* sm;
+  __device__ void operator()(double x, double& logf, double& dlogf) const {
+    const double w = exp(x);
+    const double sdu = (x - s) / eta;
+    const double wnu = w * nu;
+    double a = 0, c = 0;
+    for (int j = threadIdx.x; j < p; j += blockDim.x) {
+      const double t = vd[j] + wnu;
+      a += wnu / t;
+      c += log(t);
+    }
+    a = block_sum(a, sm);
+    c = block_sum(c, sm);
+    dlogf = a;
+    logf = c;
+    logf *= (-(nu + K) / 2);
+    dlogf *= (-(nu + K) / 2);
+    logf += p * nu / 2 * x;
+    dlogf += p * nu / 2;
+    logf += -(sdu * sdu) / 2 - log(eta);
+    dlogf += -sdu / eta;
+  }
+};
+
+__global__ void __launch_bounds__(1024) k_logw(Geom g, Bufs b) {
+  Ctl* ctl = b.ctl;
+  __shared__ double sm[32];
+  if (!(ctl->eta > 1e-10)) return;
+  if (ctl->eta < 0.01) {
+    if (threadIdx.x == 0) ctl->logw = ctl->s;
+    return;
+  }
+  LogwEval ev{b.var_deltas + 1, ctl->p, (double)ctl->K, ctl->alpha, ctl->s, ctl->eta, sm};
+  double x = 0;
+  int status;
+  const double x0 = ctl->logw;
+  if (ctl->rng_mode == 1) {
+    const long long blk = ctl->step_in_call * (long long)(ctl->p + 1) + ctl->p;
+    ArsArrayUniforms un{b.inj_ars + blk * ctl->ars_width, blk < ctl->n_ars_blocks ? ctl->ars_width : 0, 0};
+    ArsWarp<LogwEval, ArsArrayUniforms> ars(ev, un);
+    status = ars.sample(x0, x);
+  } else {
+    ArsKeyedUniforms un{ctl->seed, ctl->step, kRngLogwArs, 0u, 0u};
+    ArsWarp<LogwEval, ArsKeyedUniforms> ars(ev, un);
+    status = ars.sample(x0, x);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (status != kArsOk) { set_err(ctl, status == kArsNoUniforms ? kErrInjectArs : kErrArs, status); x = NAN; }
+    ctl->logw = x;
+  }
+}
+
+// Standalone batch (test hook / htlr_cuda_ars).
+__global__ void __launch_bounds__(256) k_ars_batch(int kind, int m, const double* vard, double K, double alpha,
+                                                    double log_aw, const double* uniforms, int width,
+                                                    unsigned long long seed, unsigned long long step, double* x_out,
+                                                    int* n_unif, int* n_eval, int* status_out) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int q = warp; q < m; q += nwarps) {
+    SgmTarget tg{kind, vard[q], K, alpha, log_aw};
+    const double x0 = log(tg.v / tg.K);
+    double x = NAN;
+    int status, nu, ne;
+    if (uniforms) {
+      ArsArrayUniforms un{uniforms + (long long)q * width, width, 0};
+      ArsWarp<SgmTarget, ArsArrayUniforms> ars(tg, un);
+      status = ars.sample(x0, x);
+      nu = ars.n_unif; ne = ars.n_eval;
+    } else {
+      ArsKeyedUniforms un{seed, step, kRngArs, (uint32_t)(q + 1), 0u};
+      ArsWarp<SgmTarget, ArsKeyedUniforms> ars(tg, un);
+      status = ars.sample(x0, x);
+      nu = ars.n_unif; ne = ars.n_eval;
+    }
+    if (lane == 0) {
+      x_out[q] = status == kArsOk ? x : NAN;
+      if (n_unif) n_unif[q] = nu;
+      if (n_eval) n_eval[q] = ne;
+      if (status_out) status_out[q] = status;
+    }
+  }
+}
+
+__global__ void k_rng_dump(unsigned long long seed, unsigned int purpose, unsigned long long step, int n_a, int n_b,
+                           int kind, double shape, double* out) {
+  const KeyedRng rng{seed};
+  const long long tot = (long long)n_a * n_b;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < tot; e += (long long)gridDim.x * blockDim.x) {
+    const uint32_t a = (uint32_t)(e / n_b), bb = (uint32_t)(e % n_b);
+    double v;
+    if (kind == 0) v = rng.unif(purpose, step, a, bb);
+    else if (kind == 1) v = rng.norm(purpose, step, a, bb);
+    else v = rng.gamma(step, a, shape);
+    out[e] = v;
+  }
+}
+
+void launch_sigma(const Geom& g, const Bufs& b, cudaStream_t st) {
+  // ptype is fixed for the life of the handle; the host picks the kernel
+  k_sigma_t<<<g.e_grid, 256, 0, st>>>(g, b);
+}
+void launch_sigma_ars(const Geom& g, const Bufs& b, cudaStream_t st) {
+  const int p = g.nvar - 1;
+  int blocks = (p + 7) / 8;
+  if (blocks > g.sm_count * 8) blocks = g.sm_count * 8;
+  if (blocks < 1) blocks = 1;
+  k_sigma_ars<<<blocks, 256, 0, st>>>(g, b);
+}
+void launch_logw(const Geom& g, const Bufs& b, cudaStream_t st) { k_logw<<<1, 1024, 0, st>>>(g, b); }
+
+void launch_ars_standalone(int kind, int m, const double* vard, double K, double alpha, double log_aw,
+                           const double* uniforms, int width, unsigned long long seed, unsigned long long step,
+                           double* x_out, int* n_unif, int* n_eval, int* status, cudaStream_t st) {
+  int blocks = (m + 7) / 8;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  k_ars_batch<<<blocks, 256, 0, st>>>(kind, m, vard, K, alpha, log_aw, uniforms, width, seed, step, x_out, n_unif,
+                                      n_eval, status);
+}
+void launch_rng_dump(unsigned long long seed, unsigned int purpose, unsigned long long step, int n_a, int n_b,
+                     int kind, double shape, double* out, cudaStream_t st) {
+  k_rng_dump<<<256, 256, 0, st>>>(seed, purpose, step, n_a, n_b, kind, shape, out);
+}
+
+}  // namespace htlr

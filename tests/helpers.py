@@ -1,0 +1,45 @@
+"""Shared problem builders for the parity tests (small shapes the CPU oracle finishes in seconds)."""
+import numpy as np
+
+from htlr_b200 import synth
+
+DEFAULTS = dict(alpha=1.0, s=-10.0, eta=0.0, iters_rmc=6, iters_h=6, thin=1, leap_L=7, leap_L_h=3, leap_step=0.3,
+                hmc_sgmcut=0.05, keep_warmup_hist=False, silence=1, legacy=False)
+
+
+def relerr(a, b):
+    """Norm-wise relative error, the measure north_star's 1e-10 gate is stated in."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    den = np.max(np.abs(b))
+    return float(np.max(np.abs(a - b)) / (den if den > 0 else 1.0))
+
+
+def problem(n, p, C, seed=0, init="random", ptype="t", scale=0.5, **over):
+    """A seeded MLR problem in htlr_fit_helper argument form."""
+    d = synth.gendata_mlr(n, p, NC=C, seed=seed)
+    y = d["y"].copy()
+    y[:C] = np.arange(C)  # every class present
+    X, ymat, ybase, K = synth.make_inputs(d["X"], y)
+    g = np.random.default_rng(seed + 1000)
+    if init == "random":
+        deltas = np.asfortranarray(g.standard_normal((p + 1, K)) * scale)
+    else:
+        deltas = np.zeros((p + 1, K), order="F")
+    v = synth.comp_vardeltas(deltas)[1:]
+    sig = np.r_[2000.0, (np.exp(-10.0) + v) / 2 / g.gamma((1 + K) / 2, size=p)]
+    args = dict(DEFAULTS)
+    args.update(p=p, K=K, n=n, X=X, ymat=ymat, ybase=ybase, ptype=ptype, deltas=deltas, sigmasbt=sig)
+    args.update(over)
+    return args
+
+
+def streams(args, seed=0, ars_width=0):
+    """Injected variates sized for a whole run, reference consumption order."""
+    g = np.random.default_rng(seed + 2000)
+    T = (args["iters_h"] + args["iters_rmc"]) * args["thin"]
+    p, K = args["p"], args["K"]
+    out = dict(normals=g.standard_normal(T * (p + 1) * K), uniforms=g.random(T),
+               gammas=g.gamma((args["alpha"] + K) / 2, size=T * p))
+    if ars_width:
+        out["ars_uniforms"] = g.random((T * (p + 1), ars_width))
+    return out
