@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""Benchmark of the HTLR sampler hot path on B200: MCMC iterations/sec + X-sweep HBM roofline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+One "step" = one sampling-phase MCMC iteration (gibbs.cpp:57-125 with L = leap = 50 leapfrog steps):
+restricted-set selection, momenta, trajectory (X sweeps, softmax, gradient), Metropolis test, per-feature
+variance update, trace recording. Workloads (BASELINE.json configs):
+
+  C_full     gendata_FAM n=1000 p=20000 C=3, t prior df=1, htlr() defaults except cut=0: every feature is
+             updated every iteration, so each leapfrog step sweeps all 160 MB of X (> 126 MB L2). This is
+             the regime that exposes the HBM roofline north_star quotes; the default workload.
+  C_default  same data, htlr() defaults (cut=0.05): restricted regime, latency-bound. Always measured too
+             and reported in the "default_cut" block of the same line, with its own CPU baseline.
+  B / D      gendata_MLR n=500 p=5000 C=4 / n=200 p=50000 C=2 (one chain).
+
+N > 1 (torchrun): independent chains, one per GPU, no communication (SURVEY 8e "replicas"); value is
+the sum over ranks. Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "C_full": dict(gen="fam", n=1000, p=20000, C=3, cut=0.0, seed=1003,
+                   desc="gendata_FAM n=1000 p=20000 C=3, t prior df=1, leap=50, cut=0 (all features updated: full X sweep per leapfrog step)"),
+    "C_default": dict(gen="fam", n=1000, p=20000, C=3, cut=0.05, seed=1003,
+                      desc="gendata_FAM n=1000 p=20000 C=3, t prior df=1, leap=50, cut=0.05 (htlr() defaults, restricted regime)"),
+    "B": dict(gen="mlr", n=500, p=5000, C=4, cut=0.0, seed=1002,
+              desc="gendata_MLR n=500 p=5000 C=4, t prior df=1, leap=50, cut=0"),
+    "D": dict(gen="mlr", n=200, p=50000, C=2, cut=0.0, seed=1004,
+              desc="gendata_MLR n=200 p=50000 C=2, t prior df=1, leap=50, cut=0 (one chain)"),
+    "tiny": dict(gen="mlr", n=120, p=400, C=3, cut=0.0, seed=5, desc="tiny smoke workload"),
+}
+HTLR_DEFAULTS = dict(ptype="t", alpha=1.0, s=-10.0, eta=0.0, thin=1, leap_L=50, leap_L_h=5, leap_step=0.3,
+                     keep_warmup_hist=False, silence=1, legacy=False)
+
+
+def make_problem(wl, chain_seed=0):
+    from htlr_b200 import synth
+    w = WORKLOADS[wl]
+    if w["gen"] == "fam":
+        d = synth.gendata_fam(w["n"], w["p"], sd_g=0.5, stdx=True, seed=w["seed"])
+    else:
+        d = synth.gendata_mlr(w["n"], w["p"], NC=w["C"], seed=w["seed"])
+        d["y"][:w["C"]] = np.arange(w["C"])
+    X, ymat, ybase, K = synth.make_inputs(d["X"], d["y"])
+    deltas, sig = synth.init_state(w["p"], K, init="zero", seed=w["seed"] + 17 + chain_seed)
+    return dict(p=w["p"], K=K, n=w["n"], X=X, ymat=ymat, ybase=ybase, deltas=deltas, sigmasbt=sig,
+                hmc_sgmcut=w["cut"], **HTLR_DEFAULTS)
+
+
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(kernel_key):
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full summary, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(kernel_key)
+    except Exception:
+        return None
+
+
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference_rate(wl, max_iters, budget_s, warm_iters):
+    """The reference's CPU sampler on this box's host cores, single thread (its hot loops are
+    single-threaded): oracle/_ref (reference sources compiled verbatim against the API
+    shims) when it was built, else the oracle port. Time-boxed sample of the same workload."""
+    from oracle import oracle as O
+    args = make_problem(wl)
+    if O.have_ref():
+        kind = "reference"
+        def fit(iters_h, iters_rmc):
+            a = dict(args, iters_h=iters_h, iters_rmc=iters_rmc)
+            return O.ref_fit(**a)["secs"]
+        base = fit(warm_iters, 1)                      # setup + warm-up + 1 sampling iteration
+        m = int(max(1, min(max_iters, (budget_s - base) / max(base, 1e-3) - 1)))
+        tm = fit(warm_iters, 1 + m) - base             # m more sampling iterations of the same chain
+        rate = m / max(tm, 1e-9)
+    else:
+        kind = "port"
+        f = O.OracleFit(**dict(args, iters_h=warm_iters, iters_rmc=max_iters))
+        f.set_seed(1)
+        f.initialize()
+        if warm_iters:
+            f.run(warm_iters)
+        m, tm = 0, 0.0
+        while m < max_iters and tm < budget_s:
+            tm += f.run(1)
+            m += 1
+        rate = m / tm
+    return rate, kind, m
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = WORKLOADS[a.workload]
+    warm = 0 if w["cut"] <= 0 else 150
+    rate, kind, m = cpu_reference_rate(a.workload, a.steps, budget_s=150.0, warm_iters=warm)
+    cores = os.cpu_count()
+    line = {"impl": "reference", "metric": "mcmc_iterations_per_sec", "value": rate, "unit": "it/s",
+            "n_gpus": a.gpus, "steps": m, "warmup": warm, "ms_per_step": 1e3 / rate, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": w["desc"], "regime": "full" if w["cut"] <= 0 else "restricted"},
+            "cpu_baseline": {"value": rate, "unit": "it/s", "cores": 1, "kind": kind,
+                             "sample": f"{m} sampling iterations (L=50) of the same workload, time-boxed to ~150 s; "
+                                       f"single thread of {cores} host cores (the reference's hot loops are single-threaded)"},
+            "e2e": {"value": rate, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------
+def time_chain(torch, smp, steps, dist=None):
+    """K iterations enqueued back to back, CUDA events on the library's own stream."""
+    st = torch.cuda.ExternalStream(smp.stream)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    smp.sync()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0.record(st)
+    smp.run_async(steps)
+    e1.record(st)
+    smp.sync()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    return e0.elapsed_time(e1)  # ms
+
+
+def measure_workload(torch, wl, steps, warmup, device, chain_seed, dist, want_profile=True):
+    import htlr_b200
+    w = WORKLOADS[wl]
+    args = make_problem(wl, chain_seed)
+    warm_iters = 0 if w["cut"] <= 0 else 150   # restricted regime: let the restricted set settle first
+    total = warm_iters + warmup + steps
+    prof_steps = min(steps, 20) if want_profile else 0
+    smp = htlr_b200.Sampler(**dict(args, iters_h=warm_iters, iters_rmc=total + prof_steps), device=device,
+                            seed=1000 + chain_seed)
+    if warm_iters:
+        smp.run(warm_iters)
+    st_w = smp.run(max(warmup, 3))
+    l0 = smp.launch_count
+    ms = time_chain(torch, smp, steps, dist)
+    launches = smp.launch_count - l0
+    res = {"ms": ms, "launches": launches}
+    if want_profile:
+        smp.profile_enable(True)
+        smp.profile_get(reset=True)
+        smp.run(prof_steps)
+        res["prof"] = smp.profile_get()
+        res["prof_steps"] = prof_steps
+        smp.profile_enable(False)
+    out = smp.fetch()
+    lo = max(warmup, 3) + 1   # trace slot of the first timed iteration (slot 0 is the initial state)
+    res["uvar"] = float(np.mean(out["mcuvar"][lo:lo + steps]))
+    res["rej"] = float(np.mean(out["mchmcrej"][lo:lo + steps]))
+    res["n"], res["p"], res["K"] = args["n"], args["p"], args["K"]
+    smp.close()
+    return res
+
+
+def measure_e2e(torch, wl, steps, device, chain_seed, dist):
+    """Same metric through the public API with HOST buffers: one htlr_fit_helper call = H2D of X / ymat /
+    initial state from pinned host memory, `steps` sampling iterations, D2H of the whole trace."""
+    import htlr_b200
+    args = make_problem(wl, chain_seed)
+    Xp = torch.from_numpy(np.ascontiguousarray(args["X"].T)).pin_memory()   # column-major storage, pinned
+    args["X"] = Xp.numpy().T
+    w = WORKLOADS[wl]
+    warm_iters = 0 if w["cut"] <= 0 else 150
+    a = dict(args, iters_h=warm_iters, iters_rmc=steps)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = htlr_b200.htlr_fit_helper(**a, device=device, seed=2000 + chain_seed)
+    t1 = time.perf_counter()
+    nvar, K, n = args["p"] + 1, args["K"], args["n"]
+    h2d = 8 * (n * nvar + n * K + n + nvar * K + nvar)
+    H = steps + 1
+    d2h = 8 * (nvar * K * H + 2 * nvar * H + 4 * H + nvar)
+    assert np.isfinite(out["mcloglike"]).all()
+    return (t1 - t0), h2d / steps, d2h / steps, warm_iters
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C_full", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the default-cut (restricted) block")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3)
+
+    if a.impl == "reference":
+        run_reference_arm(a)
+        return
+
+    import torch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: htlr_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist = dist_mod
+
+    w = WORKLOADS[a.workload]
+    clocks = ClockSampler(local)
+    clocks.start()
+    res = measure_workload(torch, a.workload, a.steps, a.warmup, local, rank, dist)
+    clk = clocks.stop()
+    e2e_s, h2d, d2h, e2e_warm = measure_e2e(torch, a.workload, a.steps, local, rank, dist)
+
+    ms = torch.tensor([res["ms"], e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_max, e2e_ms_max = float(ms[0]), float(ms[1])
+    value = world * a.steps / (ms_max * 1e-3)
+    e2e_value = world * a.steps / (e2e_ms_max * 1e-3)
+
+    secondary = None
+    if not a.no_secondary and a.workload == "C_full" and rank == 0:
+        r2 = measure_workload(torch, "C_default", max(a.steps, 200), a.warmup, local, rank, None, want_profile=True)
+        secondary = {"workload": WORKLOADS["C_default"]["desc"], "value": max(a.steps, 200) / (r2["ms"] * 1e-3),
+                     "unit": "it/s", "ms_per_step": r2["ms"] / max(a.steps, 200), "mean_nuvar": r2["uvar"],
+                     "hmc_reject": r2["rej"], "gpu_launches": r2["launches"],
+                     "kernel_time_share": (r2["prof"]["total_ms"] / r2["prof_steps"]) / (r2["ms"] / max(a.steps, 200))
+                     if r2["prof_steps"] else None,
+                     "note": "restricted regime: X[:,iup] is L2-resident, bound by launch/sync latency not HBM"}
+    if dist is not None:
+        dist.barrier()
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        pr = res["prof"]
+        ach = (pr["sweep_bytes"] / 1e9) / (pr["sweep_ms"] * 1e-3) if pr["sweep_ms"] > 0 else None
+        n, p, K = res["n"], res["p"], res["K"]
+        u = res["uvar"]
+        nvar = p + 1
+        m_detach = u if u <= nvar // 2 else nvar - u
+        L = HTLR_DEFAULTS["leap_L"]
+        bytes_two = 8.0 * n * (m_detach + u + 2 * L * u)
+        bytes_min = 8.0 * n * (m_detach + (L + 1) * u)
+        it_s_1gpu = a.steps / (res["ms"] * 1e-3)
+        line = {
+            "metric": "mcmc_iterations_per_sec", "value": value, "unit": "it/s", "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": w["desc"], "regime": "full" if w["cut"] <= 0 else "restricted",
+                       "l2": "X (%.0f MB) is larger than the 126 MB L2; no flush needed" % (8e-6 * n * nvar)
+                       if 8 * n * nvar > 126e6 else "X fits in L2 (stated; no flush: the sampler re-reads X by design)",
+                       "parallelism": "1 chain per GPU, no communication" if world > 1 else "1 chain, 1 GPU",
+                       "algorithm": "two-sweep (reference structure)", "mean_nuvar": u, "hmc_reject": res["rej"]},
+            "e2e": {"value": e2e_value, "unit": "it/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "what": "htlr_fit_helper() with pinned host buffers: H2D of X/ymat/state, %d sampling iterations "
+                            "(after %d warm-up), D2H of the full trace" % (a.steps, e2e_warm)},
+            "gpu_launches": res["launches"],
+            "clocks": clk,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": (ach / peak) if ach else None, "traffic": ncu_traffic("sweep"),
+                         "kernel": "k_lv_sweep + k_grad_sweep (X sweeps)", "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": pr["sweep_bytes"] / max(pr["sweep_launches"], 1),
+                         "launches_timed": pr["sweep_launches"], "frac_of_nominal_8TBs": (ach / 8000.0) if ach else None,
+                         "iteration_level": {"bytes_two_sweep": bytes_two, "bytes_min_one_sweep": bytes_min,
+                                             "achieved_two_sweep_GBs": bytes_two * it_s_1gpu / 1e9,
+                                             "frac_two_sweep": bytes_two * it_s_1gpu / 1e9 / peak}},
+        }
+        if secondary:
+            line["default_cut"] = secondary
+        if not a.no_cpu_baseline:
+            rate, kind, m = cpu_reference_rate(a.workload, 4, budget_s=25.0, warm_iters=0 if w["cut"] <= 0 else 150)
+            line["cpu_baseline"] = {"value": rate, "unit": "it/s", "cores": 1, "kind": kind,
+                                    "sample": f"{m} sampling iterations (L=50) of the same workload on 1 of "
+                                              f"{os.cpu_count()} host cores (reference hot loops are single-threaded)"}
+            if secondary:
+                r2c, kind2, m2 = cpu_reference_rate("C_default", 400, budget_s=15.0, warm_iters=150)
+                secondary["cpu_baseline"] = {"value": r2c, "unit": "it/s", "cores": 1, "kind": kind2,
+                                             "sample": f"{m2} sampling iterations after 150 warm-up iterations"}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -118,24 +118,21 @@ void prof_drain(htlr_handle* h) {
 }
 struct ProfScope {
   htlr_handle* h;
-  EventPair* ep = nullptr;
+  long idx = -1;  // index into ev_pool (the vector may grow while an outer scope is open)
   ProfScope(htlr_handle* hh, int kind) : h(hh) {
     if (!h->profiling) return;
     if (h->ev_used == h->ev_pool.size()) {
-      if (h->ev_pool.size() >= 16384) prof_drain(h);
-      else {
-        EventPair p{};
-        CU(cudaEventCreate(&p.a));
-        CU(cudaEventCreate(&p.b));
-        h->ev_pool.push_back(p);
-      }
+      EventPair p{};
+      CU(cudaEventCreate(&p.a));
+      CU(cudaEventCreate(&p.b));
+      h->ev_pool.push_back(p);
     }
-    ep = &h->ev_pool[h->ev_used++];
-    ep->kind = kind;
-    CU(cudaEventRecord(ep->a, h->st));
+    idx = (long)h->ev_used++;
+    h->ev_pool[idx].kind = kind;
+    CU(cudaEventRecord(h->ev_pool[idx].a, h->st));
   }
   ~ProfScope() {
-    if (ep) cudaEventRecord(ep->b, h->st);
+    if (idx >= 0) cudaEventRecord(h->ev_pool[idx].b, h->st);
   }
 };
 
@@ -520,6 +517,7 @@ static void enqueue_iters(htlr_handle* h, int32_t n_iters) {
         CU(cudaGraphLaunch(ge, h->st));
         h->launches += kernels_per_step(h, L);
       } else {
+        if (h->ev_used > 8192) prof_drain(h);
         h->launches += enqueue_step(h, L);
       }
     }
