@@ -194,6 +194,9 @@ def time_chain(torch, smp, steps, dist=None):
     return e0.elapsed_time(e1)  # ms
 
 
+ALGO = 0
+
+
 def measure_workload(torch, wl, steps, warmup, device, chain_seed, dist, want_profile=True):
     import htlr_b200
     w = WORKLOADS[wl]
@@ -202,7 +205,7 @@ def measure_workload(torch, wl, steps, warmup, device, chain_seed, dist, want_pr
     total = warm_iters + warmup + steps
     prof_steps = min(steps, 20) if want_profile else 0
     smp = htlr_b200.Sampler(**dict(args, iters_h=warm_iters, iters_rmc=total + prof_steps), device=device,
-                            seed=1000 + chain_seed)
+                            seed=1000 + chain_seed, algo=ALGO)
     if warm_iters:
         smp.run(warm_iters)
     st_w = smp.run(max(warmup, 3))
@@ -240,7 +243,7 @@ def measure_e2e(torch, wl, steps, device, chain_seed, dist):
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    out = htlr_b200.htlr_fit_helper(**a, device=device, seed=2000 + chain_seed)
+    out = htlr_b200.htlr_fit_helper(**a, device=device, seed=2000 + chain_seed, algo=ALGO)
     t1 = time.perf_counter()
     nvar, K, n = args["p"] + 1, args["K"], args["n"]
     h2d = 8 * (n * nvar + n * K + n + nvar * K + nvar)
@@ -259,8 +262,11 @@ def main():
     ap.add_argument("--workload", default="C_full", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the default-cut (restricted) block")
+    ap.add_argument("--algo", type=int, default=0, help="0 auto (fused when applicable), 1 two-sweep, 2 fused")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
+    global ALGO
+    ALGO = a.algo
 
     if a.impl == "reference":
         run_reference_arm(a)
@@ -325,7 +331,7 @@ def main():
                        "l2": "X (%.0f MB) is larger than the 126 MB L2; no flush needed" % (8e-6 * n * nvar)
                        if 8 * n * nvar > 126e6 else "X fits in L2 (stated; no flush: the sampler re-reads X by design)",
                        "parallelism": "1 chain per GPU, no communication" if world > 1 else "1 chain, 1 GPU",
-                       "algorithm": "two-sweep (reference structure)", "mean_nuvar": u, "hmc_reject": res["rej"]},
+                       "algorithm": "two-sweep (reference structure)" if a.algo == 1 else "fused one-sweep persistent trajectory kernel", "mean_nuvar": u, "hmc_reject": res["rej"]},
             "e2e": {"value": e2e_value, "unit": "it/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "what": "htlr_fit_helper() with pinned host buffers: H2D of X/ymat/state, %d sampling iterations "
                             "(after %d warm-up), D2H of the full trace" % (a.steps, e2e_warm)},
@@ -333,7 +339,7 @@ def main():
             "clocks": clk,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": (ach / peak) if ach else None, "traffic": ncu_traffic("sweep"),
-                         "kernel": "k_lv_sweep + k_grad_sweep (X sweeps)", "peak_source": peak_src,
+                         "kernel": "k_lv_sweep + k_grad_sweep (X sweeps)" if a.algo == 1 else "k_traj_fused (L+1 X sweeps per launch) + detach sweep", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": pr["sweep_bytes"] / max(pr["sweep_launches"], 1),
                          "launches_timed": pr["sweep_launches"], "frac_of_nominal_8TBs": (ach / 8000.0) if ach else None,
                          "iteration_level": {"bytes_two_sweep": bytes_two, "bytes_min_one_sweep": bytes_min,

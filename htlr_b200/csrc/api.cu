@@ -62,6 +62,8 @@ struct htlr_handle {
   std::map<int, cudaGraphExec_t> graphs;
   ncclComm_t comm = nullptr;
   bool sharded = false;
+  bool fused = false;
+  FusedGeom fg{};
   bool profiling = false;
   std::vector<EventPair> ev_pool;
   size_t ev_used = 0;
@@ -168,8 +170,14 @@ int enqueue_step(htlr_handle* h, int L, bool until_energy_only = false) {
     ++nk;
   }
   launch_softmax(g, b, 0, nullptr, nullptr, nullptr, nullptr, nullptr, st); ++nk;
-  gradient(0);
-  for (int t = 1; t <= L; ++t) {
+  if (h->fused) {
+    ProfScope ps(h, 0);
+    CU(launch_traj_fused(g, b, h->fg, L, st));
+    ++nk;
+  } else {
+    gradient(0);
+  }
+  for (int t = 1; t <= L && !h->fused; ++t) {
     {
       ProfScope ps(h, 0);
       launch_lv_sweep(g, b, 1, nullptr, nullptr, nullptr, st);
@@ -221,6 +229,7 @@ cudaGraphExec_t get_graph(htlr_handle* h, int L) {
 int kernels_per_step(const htlr_handle* h, int L) {
   int per_grad = h->sharded ? 3 : 2;
   int n = 2 + 2 + per_grad + L * (2 + per_grad) + 1 + 1 + 1 + 1;
+  if (h->fused) n = 2 + 2 + 1 + 1 + 1 + 1 + 1;
   if (h->cfg.ptype == HTLR_PRIOR_T && h->cfg.eta > 1e-10) n += 1;
   return n;
 }
@@ -371,8 +380,19 @@ void do_create(const htlr_cfg* cfg, const double* X, int64_t ldx, const double* 
   b.vdc = h->dalloc<double>(nvar);
   b.g = h->dalloc<double>((size_t)nvar * K + 1);
   b.gpart = h->dalloc<double>((size_t)g.g_rt * nvar * K);
-  b.lvpart = h->dalloc<double>((size_t)g.lv_cs * K * g.n_s);
-  b.red = h->dalloc<Red4>((size_t)std::max(std::max(g.e_grid, (n + 255) / 256), 1));
+  // ---- trajectory algorithm
+  {
+    FusedGeom fgm{};
+    int coop = 0;
+    CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c.device));
+    const bool can = coop && !h->sharded && fused_plan(g, (int)prop.sharedMemPerBlockOptin, &fgm);
+    if (c.algo == HTLR_ALGO_FUSED && !can)
+      FAIL(HTLR_E_ARG, "fused trajectory not applicable (needs K <= 4, a column tile in shared memory, one GPU)");
+    h->fused = can && c.algo != HTLR_ALGO_TWO_SWEEP;
+    h->fg = fgm;
+  }
+  b.lvpart = h->dalloc<double>((size_t)std::max(g.lv_cs, g.sm_count) * K * g.n_s);
+  b.red = h->dalloc<Red4>((size_t)std::max(std::max(g.e_grid, (n + 255) / 256), g.sm_count));
   b.ctl = h->dalloc<Ctl>(1);
 
   // ---- history

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstddef>
 #include <cstdint>
 
 #include "common.cuh"
@@ -24,6 +25,18 @@ struct Geom {
   // elementwise kernels over the restricted set
   int e_grid;
   int sm_count;
+};
+
+// Tile shape of the fused trajectory kernel (fused_kernel.cu), chosen once per handle by fused_plan().
+struct FusedGeom {
+  int T;       // columns per shared-memory tile
+  int S;       // column stride in shared memory (doubles), even, chosen bank-conflict-free
+  int NS;      // ring stages
+  int nrp;     // row pairs per thread, gradient phase
+  int nlp;     // row pairs per thread, lv phase
+  int rpc;     // rows per block in the softmax phase
+  int grid;    // blocks (= SMs)
+  size_t smem_bytes, smem_bytes_max;
 };
 
 struct Bufs {
@@ -77,6 +90,10 @@ void launch_record(const Geom& g, const Bufs& b, cudaStream_t st);
 void launch_vardeltas_all(const Geom& g, const Bufs& b, cudaStream_t st);
 void launch_scatter_proposal(const Geom& g, const Bufs& b, double* deltas_out, double* momt_out,
                              double* vd_out, cudaStream_t st);
+
+// fused_kernel.cu
+bool fused_plan(const Geom& g, int smem_optin_bytes, FusedGeom* out);
+cudaError_t launch_traj_fused(const Geom& g, const Bufs& b, const FusedGeom& fg, int L, cudaStream_t st);
 
 // sigma_kernels.cu (compiled with --fmad=false)
 void launch_sigma(const Geom& g, const Bufs& b, cudaStream_t st);      // t prior: gamma draws

@@ -50,12 +50,17 @@ def test_initial_state_matches_oracle():
     gpu.close()
 
 
+ALGOS = [pytest.param(1, id="two-sweep"), pytest.param(2, id="fused")]
+
+
+@pytest.mark.parametrize("algo", ALGOS)
 @pytest.mark.parametrize("n,p,C,L,cut", [(62, 200, 2, 5, 0.05), (300, 100, 3, 50, 0.05), (120, 80, 4, 20, 0.0),
-                                          (1000, 60, 3, 10, 0.05), (90, 400, 2, 30, 1e-3)])
-def test_trajectory_matches_oracle(n, p, C, L, cut):
+                                          (1000, 60, 3, 10, 0.05), (90, 400, 2, 30, 1e-3), (37, 900, 5, 7, 0.0),
+                                          (1999, 50, 2, 6, 0.0), (501, 3000, 3, 4, 0.0)])
+def test_trajectory_matches_oracle(n, p, C, L, cut, algo):
     """A whole leapfrog trajectory with injected identical momenta (north_star level-1 gate)."""
     args = problem(n, p, C, seed=7 * n + p, hmc_sgmcut=cut, scale=0.3)
-    gpu, ora = _pair(args)
+    gpu, ora = _pair(args, algo=algo)
     g = np.random.default_rng(11)
     momt = np.asfortranarray(g.standard_normal((p + 1, C - 1)))
     a, b = gpu.trajectory(momt, L), ora.trajectory(momt, L)
@@ -85,15 +90,16 @@ def test_trajectory_matches_oracle(n, p, C, L, cut):
     dict(n=70, p=90, C=3, thin=1, keep_warmup_hist=False, leap_step=0.9),   # plenty of rejections
     dict(n=64, p=70, C=2, thin=1, keep_warmup_hist=True, eta=0.5),           # logw ARS
 ])
+@pytest.mark.parametrize("algo", ALGOS)
 @pytest.mark.parametrize("use_graph", [False, True])
-def test_chain_t_prior_injected(cfg, use_graph):
+def test_chain_t_prior_injected(cfg, use_graph, algo):
     """Full chains, t prior, identical injected normals / uniforms / gammas: every trace matches."""
     import htlr_b200
     cfg = dict(cfg)
     n, p, C = cfg.pop("n"), cfg.pop("p"), cfg.pop("C")
     args = problem(n, p, C, seed=n * 3 + p, **cfg)
     st = streams(args, seed=n, ars_width=48 if args["eta"] > 0 else 0)
-    gpu, ora = _pair(args, rng_mode=htlr_b200.fit.RNG_INJECT, use_graph=use_graph,
+    gpu, ora = _pair(args, rng_mode=htlr_b200.fit.RNG_INJECT, use_graph=use_graph, algo=algo,
                      ars_inject_width=48 if args["eta"] > 0 else 0)
     ora.set_inject(st["normals"], st["uniforms"], st["gammas"], st.get("ars_uniforms"))
     T = args["iters_h"] + args["iters_rmc"]
@@ -110,14 +116,15 @@ def test_chain_t_prior_injected(cfg, use_graph):
     gpu.close()
 
 
+@pytest.mark.parametrize("algo", ALGOS)
 @pytest.mark.parametrize("ptype", ["ghs", "neg"])
 @pytest.mark.parametrize("C", [2, 3])
-def test_chain_ars_priors_injected(ptype, C):
+def test_chain_ars_priors_injected(ptype, C, algo):
     """ghs / neg: per-feature warp ARS fed the same per-feature uniform blocks as the CPU engine."""
     import htlr_b200
     args = problem(60, 50, C, seed=17 + C, ptype=ptype, iters_rmc=4, iters_h=4, leap_L=5)
     st = streams(args, seed=C, ars_width=64)
-    gpu, ora = _pair(args, rng_mode=htlr_b200.fit.RNG_INJECT, ars_inject_width=64)
+    gpu, ora = _pair(args, rng_mode=htlr_b200.fit.RNG_INJECT, ars_inject_width=64, algo=algo)
     ora.set_inject(st["normals"], st["uniforms"], st["gammas"], st["ars_uniforms"])
     T = args["iters_h"] + args["iters_rmc"]
     gpu.run(T, **st)
@@ -221,3 +228,28 @@ def test_fit_helper_end_to_end_shapes():
     assert out["mcdeltas"].shape == (41, 2, H) and out["mcsigmasbt"].shape == (41, H)
     assert out["mclogw"].shape == (H, 1) and out["mc.param"]["DDNloglike"].shape == (1, 41)
     assert np.isfinite(out["mcdeltas"]).all() and (out["mcuvar"][1:] >= 1).all()
+
+
+def test_fused_and_two_sweep_chains_agree():
+    """Same keyed RNG, both trajectory algorithms: identical accept decisions, traces equal to rounding."""
+    import htlr_b200
+    args = problem(400, 600, 3, seed=31, iters_rmc=6, iters_h=6, leap_L=25)
+    outs = []
+    for algo in (1, 2):
+        s = htlr_b200.Sampler(**args, seed=99, algo=algo)
+        s.run(12)
+        outs.append(s.fetch())
+        s.close()
+    assert np.array_equal(outs[0]["mcuvar"], outs[1]["mcuvar"])
+    assert np.array_equal(outs[0]["mchmcrej"], outs[1]["mchmcrej"])
+    assert relerr(outs[0]["mcdeltas"], outs[1]["mcdeltas"]) < 1e-8
+
+
+def test_fused_rejected_when_not_applicable():
+    import htlr_b200
+    args = problem(60, 40, 7, seed=3)   # K = 6 > 4
+    with pytest.raises(htlr_b200.HtlrCudaError, match="fused trajectory not applicable"):
+        htlr_b200.Sampler(**args, algo=2)
+    s = htlr_b200.Sampler(**args, algo=0)   # AUTO falls back to the two-sweep path
+    s.run(2)
+    s.close()
