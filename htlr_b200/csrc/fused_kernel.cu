@@ -9,36 +9,37 @@
 // separate subtractions (bit-compatible with the reference), drifts delta_j, and accumulates X_j delta_j
 // into its private lv partial. Algorithmic X traffic per iteration: 8 n (L+1) u bytes (+ detach).
 //
-// Structure (grid = one 512-thread block per SM, cooperative launch):
-//   * each block owns a contiguous range of restricted-set columns, split in tiles of T columns;
-//   * thread 0 streams the tiles into a shared-memory ring with cp.async.bulk (1-D TMA copies, one per
-//     column, completion on an mbarrier); the stream runs ahead across leapfrog steps, and if the
-//     block's whole range fits in the ring it is loaded once and stays resident for the trajectory;
-//   * gradient phase: lane <-> (column of the tile, row subgroup), 128-bit conflict-free transposed
-//     reads (column stride chosen so 8 consecutive lanes hit 8 distinct 16-byte bank groups), the
-//     residual rows a thread needs are held in registers for the whole sweep; no shuffles across rows
-//     except log2(32/T) steps, then a fixed-order sum over the 16 warps;
-//   * post phase: T threads apply prior gradient, kicks and drift (un-fused products);
-//   * lv phase: thread <-> two consecutive rows, loop over the tile's columns;
-//   * after the sweep the per-block lv partials are summed in block order (deterministic), rows are
-//     soft-maxed and the new residual published — two grid-wide syncs per leapfrog step.
-#include <cooperative_groups.h>
-
+// Structure: grid = one block per SM (cooperative launch), 18 warps with fixed roles that hand tiles to
+// each other through mbarriers only (no block-wide barrier in the steady state):
+//   warp 0      producer — streams this block's column tiles (T columns x n rows) into a shared-memory
+//               ring with cp.async.bulk (1-D TMA copies, one lane per column, completion counted on the
+//               stage's `full` mbarrier). It runs ahead across leapfrog steps, so the ring is full again
+//               when the block comes back from the grid-wide reduction; if the block's whole column range
+//               fits in the ring it is loaded once and stays resident for the whole trajectory.
+//   warp 1      post — for each tile sums the 16 per-warp gradient partials in fixed order, adds the prior
+//               gradient, applies MoveMomt / UpdateMomtAndDeltas (un-fused products) and publishes the
+//               tile's new coefficients.
+//   warps 2-17  compute — gradient phase: lane <-> (column of the tile, row subgroup), 128-bit
+//               conflict-free transposed reads (column stride chosen so 8 consecutive lanes hit 8 distinct
+//               16-byte bank groups), the residual rows a thread needs live in registers for the sweep;
+//               lv phase (one tile behind, so the post warp is off the critical path): thread <-> two
+//               consecutive rows, loop over the tile's columns.
+// After each sweep the per-block lv partials are summed in block order (deterministic), rows are
+// soft-maxed and the new residual is published: two grid-wide barriers per leapfrog step.
 #include <algorithm>
 #include <cstdio>
 
 #include "common.cuh"
 #include "launch.h"
 
-namespace cg = cooperative_groups;
-
 namespace htlr {
 
 namespace {
 
-constexpr int kFW = 16;          // warps per block
-constexpr int kFT = kFW * 32;    // threads per block
-constexpr int kNlpMax = 2;       // row pairs per thread in the lv phase (n <= 2048)
+constexpr int kCW = 16;                 // compute warps
+constexpr int kCT = kCW * 32;           // compute threads
+constexpr int kFT = kCT + 64;           // + producer warp + post warp
+constexpr int kNlpMax = 2;              // row pairs per compute thread in the lv phase (n <= 2048)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -46,6 +47,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -69,10 +73,31 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {}
 }
+__device__ __forceinline__ void named_bar(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Grid-wide barrier over all kFT threads of every block (blocks are co-resident: cooperative launch).
+// `counter` only ever grows during one launch; it is zeroed by k_begin before every trajectory.
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& gen, unsigned nblocks) {
+  named_bar(1, kFT);  // orders every thread's prior writes before thread 0's release below
+  if (threadIdx.x == 0) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+    const unsigned target = (gen + 1) * nblocks;
+    while (ld_acquire(counter) < target) { __nanosleep(32); }
+  }
+  named_bar(1, kFT);
+  ++gen;
+}
 
 template <int KT>
 struct NrpMax {
-  static constexpr int v = KT <= 2 ? 8 : 4;
+  static constexpr int v = 4;  // row pairs per compute thread in the gradient phase (registers: 2*4*K doubles)
 };
 
 }  // namespace
@@ -81,26 +106,33 @@ template <int KT, int TT>
 __global__ void __launch_bounds__(kFT, 1) k_traj_fused(Geom g, Bufs b, FusedGeom fg, int L) {
   constexpr int RS = 32 / TT;            // row subgroups per warp in the gradient phase
   constexpr int NRPM = NrpMax<KT>::v;    // row pairs a thread covers in the gradient phase (max)
-  cg::grid_group grid = cg::this_grid();
   Ctl* ctl = b.ctl;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int S = fg.S;
+  const int S = fg.S, NS = fg.NS;
   double* ring = reinterpret_cast<double*>(smem_raw);                      // [NS][TT][S]
-  double* gw = ring + (size_t)fg.NS * TT * S;                               // [kFW][TT*KT]
-  double* dts = gw + kFW * TT * KT;                                         // [TT*KT]
-  double* redsm = dts + TT * KT;                                            // [32]
-  double* dl = redsm + 32;                                                  // [rpc*KT]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(dl + fg.rpc * KT);           // [NS]
+  double* gw = ring + (size_t)NS * TT * S;                                  // [2][kCW][TT*KT]
+  double* dts = gw + 2 * kCW * TT * KT;                                     // [2][TT*KT]
+  double* redsm = dts + 2 * TT * KT;                                        // [kCW]
+  double* dl = redsm + kCW;                                                 // [rpc*KT]
+  double* cst = dl + fg.rpc * KT;                     // per-column state of this block: [ncmax][2*KT+2] = d, m, sig, step
+  uint64_t* bars = reinterpret_cast<uint64_t*>(cst + (size_t)fg.ncmax * (2 * KT + 2));
+  uint64_t* full = bars;            // [NS]  producer -> compute
+  uint64_t* empty = bars + NS;      // [NS]  compute  -> producer
+  uint64_t* gdone = empty + NS;     // [2]   compute  -> post
+  uint64_t* pdone = gdone + 2;      // [2]   post     -> compute
+  int* cidx = reinterpret_cast<int*>(pdone + 2);      // [ncmax] X column of each owned restricted-set position
 
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const int G = gridDim.x, cta = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned G = gridDim.x;
+  const int cta = blockIdx.x;
   const int n = g.n, n_s = g.n_s, npairs = (n + 1) >> 1;
   const int u = ctl->u;
-  const double Cd = (double)ctl->C;
+  unsigned* gcounter = &ctl->ticket[4];
+  unsigned gen = 0;
 
   // ---- column ownership: whole tiles, contiguous, only as many blocks as there are tiles
   const int tiles_total = (u + TT - 1) / TT;
-  const int gact = min(G, tiles_total);
+  const int gact = min((int)G, tiles_total);
   int t0 = 0, t1 = 0;
   if (cta < gact) {
     t0 = (int)((int64_t)cta * tiles_total / gact);
@@ -108,211 +140,288 @@ __global__ void __launch_bounds__(kFT, 1) k_traj_fused(Geom g, Bufs b, FusedGeom
   }
   const int ntile = t1 - t0;
   const int c0 = t0 * TT, c1 = min(u, t1 * TT);
-  const bool resident = ntile <= fg.NS;
+  const bool resident = ntile <= NS;
   const int64_t total_loads = resident ? ntile : (int64_t)ntile * (L + 1);
   const uint32_t col_bytes = (uint32_t)(((n + 1) >> 1) << 4);  // n rounded up to even, in bytes
 
   if (tid == 0) {
-    for (int sidx = 0; sidx < fg.NS; ++sidx) mbar_init(&bars[sidx], 1);
+    for (int i = 0; i < NS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], kCW); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&gdone[i], kCW); mbar_init(&pdone[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (cta == 0) ctl->cols_swept += (unsigned long long)u * (unsigned long long)(L + 1);
+  }
+  // this block's column indices and per-column state live in shared memory for the whole trajectory
+  constexpr int CS = 2 * KT + 2;
+  for (int e = tid; e < c1 - c0; e += kFT) {
+    const int r = c0 + e;
+    cidx[e] = b.iup[r];
+    double* st = cst + (size_t)e * CS;
+#pragma unroll
+    for (int k = 0; k < KT; ++k) { st[k] = b.dc[(int64_t)r * KT + k]; st[KT + k] = b.momt[(int64_t)r * KT + k]; }
+    st[2 * KT] = b.sigc[r];
+    st[2 * KT + 1] = b.stepc[r];
   }
   __syncthreads();
 
-  auto issue = [&](int64_t q) {  // thread 0 only
-    const int ti = (int)(q % ntile), stage = (int)(q % fg.NS);
-    const int r0 = c0 + ti * TT;
-    const int ncol = min(TT, c1 - r0);
-    mbar_expect_tx(&bars[stage], col_bytes * (uint32_t)ncol);
-    double* dst = ring + (size_t)stage * TT * S;
-    for (int jj = 0; jj < ncol; ++jj) {
-      const int j = b.iup[r0 + jj];
-      bulk_g2s(dst + (size_t)jj * S, b.X + (int64_t)j * g.ld, col_bytes, &bars[stage]);
-    }
-  };
-  if (tid == 0) {
-    const int64_t pre = total_loads < fg.NS ? total_loads : fg.NS;
-    for (int64_t q = 0; q < pre; ++q) issue(q);
-    if (cta == 0) ctl->cols_swept += (unsigned long long)u * (unsigned long long)(L + 1);
-  }
-
-  // gradient-phase coordinates
-  const int gj = lane % TT, grs = lane / TT;
-  double Rg[NRPM][2][KT];
-  int64_t q = 0;  // running tile counter of this block (ring position)
-
-  for (int s = 0; s <= L; ++s) {
-    // ---- residual rows of this thread into registers (published by the previous softmax phase)
-#pragma unroll
-    for (int m = 0; m < NRPM; ++m) {
-      const int rp = grs + RS * (w + kFW * m);
-#pragma unroll
-      for (int k = 0; k < KT; ++k) {
-        double r0 = 0, r1 = 0;
-        if (m < fg.nrp && rp < npairs) {
-          const double* Rk = b.R + (int64_t)k * n_s + 2 * rp;
-          r0 = __ldcg(Rk);
-          r1 = (2 * rp + 1 < n) ? __ldcg(Rk + 1) : 0.0;
-        }
-        Rg[m][0][k] = r0;
-        Rg[m][1][k] = r1;
+  if (warp == 0) {
+    // ================================ producer ================================
+    int64_t issued = 0;
+    for (int s = 0; s <= L; ++s) {
+      int64_t limit;
+      if (resident) limit = ntile;
+      else {
+        limit = (int64_t)(s + 1) * ntile + (s < L ? min(NS, ntile) : 0);
+        if (limit > total_loads) limit = total_loads;
       }
+      for (; issued < limit; ++issued) {
+        const int64_t q = issued;
+        const int ti = (int)(q % ntile), stage = (int)(q % NS);
+        if (q >= NS) mbar_wait(&empty[stage], (uint32_t)(((q / NS) - 1) & 1));
+        const int r0 = c0 + ti * TT;
+        const int ncol = min(TT, c1 - r0);
+        if (lane == 0) mbar_expect_tx(&full[stage], col_bytes * (uint32_t)ncol);
+        __syncwarp();
+        if (lane < ncol) {
+          const int j = cidx[r0 - c0 + lane];
+          bulk_g2s(ring + ((size_t)stage * TT + lane) * S, b.X + (int64_t)j * g.ld, col_bytes, &full[stage]);
+        }
+      }
+      if (s < L) { grid_barrier(gcounter, gen, G); grid_barrier(gcounter, gen, G); }
     }
-    double la[kNlpMax][2][KT];
+  } else if (warp == 1) {
+    // ================================ post ================================
+    // lane <-> (column jj, class k, quarter qt of the compute warps): 4 partial sums each, combined in a
+    // fixed order with two shuffles, so the 16-warp gradient sum costs ~6 dependent adds, not 16.
+    const double Cd = (double)ctl->C;
+    constexpr int PER = TT * KT;                 // (column, class) pairs per tile
+    constexpr int ROUNDS = (PER * 4 + 31) / 32;  // 8 pairs per round
+    int64_t tc = 0;  // tiles processed by this block so far (parity of gdone / pdone)
+    for (int s = 0; s <= L; ++s) {
+      for (int ti = 0; ti < ntile; ++ti, ++tc) {
+        const int bsel = (int)(tc & 1);
+        const uint32_t par = (uint32_t)((tc >> 1) & 1);
+        const int e0 = ti * TT;                 // first owned column of the tile (block-local)
+        const int ncol = min(TT, (c1 - c0) - e0);
+        mbar_wait(&gdone[bsel], par);
+        const double* gwb = gw + (size_t)bsel * kCW * PER;
+        double* dtb = dts + bsel * PER;
 #pragma unroll
-    for (int pp = 0; pp < kNlpMax; ++pp)
+        for (int rd = 0; rd < ROUNDS; ++rd) {
+          const int pr = rd * 8 + (lane >> 2), qt = lane & 3;   // pair index, quarter
+          const int jj = pr / KT, k = pr - jj * KT;
+          double gl = 0;
+          if (pr < PER) {
 #pragma unroll
-      for (int k = 0; k < KT; ++k) { la[pp][0][k] = 0; la[pp][1][k] = 0; }
-
-    for (int ti = 0; ti < ntile; ++ti, ++q) {
-      const int64_t qq = resident ? ti : q;
-      const int stage = (int)(qq % fg.NS);
-      if (!resident || s == 0) mbar_wait(&bars[stage], (uint32_t)((qq / fg.NS) & 1));
-      const double* tile = ring + (size_t)stage * TT * S;
-      const int r0 = c0 + ti * TT;
-      const int ncol = min(TT, c1 - r0);
-
-      // ---- gradient phase
-      double acc[KT];
+            for (int ww = 0; ww < 4; ++ww) gl += gwb[(qt * 4 + ww) * PER + pr];
+          }
+          gl += __shfl_xor_sync(0xffffffffu, gl, 1);
+          gl += __shfl_xor_sync(0xffffffffu, gl, 2);
+          if (pr < PER && jj < ncol && qt == 0) {
+            double* st = cst + (size_t)(e0 + jj) * CS;
+            double sd = st[0];
 #pragma unroll
-      for (int k = 0; k < KT; ++k) acc[k] = 0;
-      if (gj < ncol) {
-        const double* xc = tile + (size_t)gj * S;
-#pragma unroll
-        for (int m = 0; m < NRPM; ++m) {
-          const int rp = grs + RS * (w + kFW * m);
-          if (m < fg.nrp && rp < npairs) {
-            double2 x = *reinterpret_cast<const double2*>(xc + 2 * rp);
-            if (2 * rp + 1 >= n) x.y = 0;
-#pragma unroll
-            for (int k = 0; k < KT; ++k) acc[k] = fma(x.x, Rg[m][0][k], fma(x.y, Rg[m][1][k], acc[k]));
+            for (int kk = 1; kk < KT; ++kk) sd += st[kk];
+            const double sig = st[2 * KT], stp = st[2 * KT + 1], hs = stp / 2;
+            const double dold = st[k];
+            const double post = gl + (dold - sd / Cd) / sig;
+            double m = st[KT + k];
+            const double kick = __dmul_rn(hs, post);
+            if (s >= 1) m = __dsub_rn(m, kick);
+            double dnew = dold;
+            if (s < L) {
+              m = __dsub_rn(m, kick);
+              dnew = __dadd_rn(dold, __dmul_rn(stp, m));
+            }
+            dtb[pr] = dnew;
+            st[KT + k] = m;  // momenta are private to (column, class); deltas are committed below
           }
         }
+        __syncwarp();
+        // commit the new deltas of this tile to the column state (after every lane has read the old ones)
+        for (int pr = lane; pr < ncol * KT; pr += 32) {
+          const int jj = pr / KT, k = pr - jj * KT;
+          cst[(size_t)(e0 + jj) * CS + k] = dtb[pr];
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&pdone[bsel]);
       }
+      if (s < L) { grid_barrier(gcounter, gen, G); grid_barrier(gcounter, gen, G); }
+    }
+    // final coefficients and momenta back to the compact global arrays
+    for (int e = lane; e < c1 - c0; e += 32) {
+      const int r = c0 + e;
+      const double* st = cst + (size_t)e * CS;
 #pragma unroll
-      for (int o = TT; o < 32; o <<= 1)
+      for (int k = 0; k < KT; ++k) { b.dc[(int64_t)r * KT + k] = st[k]; b.momt[(int64_t)r * KT + k] = st[KT + k]; }
+    }
+  } else {
+    // ================================ compute ================================
+    const int ct = tid - 64, w = warp - 2;
+    const int gj = lane % TT, grs = lane / TT;
+    double Rg[NRPM][2][KT];
+    int64_t tc = 0;   // tile counter (gdone / pdone parity), same sequence as the post warp's
+    int64_t q = 0;    // ring position counter
+    for (int s = 0; s <= L; ++s) {
+      // residual rows of this thread into registers (published by the previous softmax phase)
 #pragma unroll
-        for (int k = 0; k < KT; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
-      if (lane < TT)
-#pragma unroll
-        for (int k = 0; k < KT; ++k) gw[(w * TT + lane) * KT + k] = acc[k];
-      __syncthreads();
-
-      // the ring slot consumed by the previous tile is free now: refill it (stream runs ahead across steps)
-      if (tid == 0 && !resident && q >= 1) {
-        const int64_t nxt = q - 1 + fg.NS;
-        if (nxt < total_loads) issue(nxt);
-      }
-
-      // ---- post phase: prior gradient, MoveMomt of step s, UpdateMomtAndDeltas of step s+1
-      if (tid < ncol) {
-        const int r = r0 + tid;
-        double* d = b.dc + (int64_t)r * KT;
-        double* mo = b.momt + (int64_t)r * KT;
-        const double sig = b.sigc[r], stp = b.stepc[r], hs = stp / 2;
-        double dv[KT];
-        double sd = 0;
-#pragma unroll
-        for (int k = 0; k < KT; ++k) { dv[k] = d[k]; sd = (k == 0) ? dv[0] : sd + dv[k]; }
-        const double sdc = sd / Cd;
+      for (int m = 0; m < NRPM; ++m) {
+        const int rp = grs + RS * (w + kCW * m);
 #pragma unroll
         for (int k = 0; k < KT; ++k) {
-          double gl = 0;
-#pragma unroll
-          for (int ww = 0; ww < kFW; ++ww) gl += gw[(ww * TT + tid) * KT + k];
-          const double post = gl + (dv[k] - sdc) / sig;
-          double m = mo[k];
-          const double kick = __dmul_rn(hs, post);
-          if (s >= 1) m = __dsub_rn(m, kick);
-          if (s < L) {
-            m = __dsub_rn(m, kick);
-            dv[k] = __dadd_rn(dv[k], __dmul_rn(stp, m));
-            d[k] = dv[k];
+          double r0v = 0, r1v = 0;
+          if (m < fg.nrp && rp < npairs) {
+            const double* Rk = b.R + (int64_t)k * n_s + 2 * rp;
+            r0v = __ldcg(Rk);
+            r1v = (2 * rp + 1 < n) ? __ldcg(Rk + 1) : 0.0;
           }
-          mo[k] = m;
-          dts[tid * KT + k] = dv[k];
+          Rg[m][0][k] = r0v;
+          Rg[m][1][k] = r1v;
         }
       }
-      __syncthreads();
+      double la[kNlpMax][2][KT];
+#pragma unroll
+      for (int pp = 0; pp < kNlpMax; ++pp)
+#pragma unroll
+        for (int k = 0; k < KT; ++k) { la[pp][0][k] = 0; la[pp][1][k] = 0; }
 
-      // ---- lv phase: this block's partial of X[:, iup] * delta
-      if (s < L) {
+      // lv phase of one tile (runs one tile behind the gradient phase)
+      auto lv_phase = [&](int ti_prev, int64_t tc_prev, int64_t q_prev) {
+        const int bsel = (int)(tc_prev & 1);
+        mbar_wait(&pdone[bsel], (uint32_t)((tc_prev >> 1) & 1));
+        const int stage = (int)((resident ? ti_prev : q_prev) % NS);
+        if (s < L) {
+          const double* tile = ring + (size_t)stage * TT * S;
+          const double* dtb = dts + bsel * TT * KT;
+          const int ncol = min(TT, c1 - (c0 + ti_prev * TT));
 #pragma unroll
-        for (int pp = 0; pp < kNlpMax; ++pp) {
-          const int rp = tid + kFT * pp;
-          if (pp < fg.nlp && rp < npairs) {
-            for (int jj = 0; jj < ncol; ++jj) {
-              const double2 x = *reinterpret_cast<const double2*>(tile + (size_t)jj * S + 2 * rp);
+          for (int pp = 0; pp < kNlpMax; ++pp) {
+            const int rp = ct + kCT * pp;
+            if (pp < fg.nlp && rp < npairs) {
+              for (int jj = 0; jj < ncol; ++jj) {
+                const double2 x = *reinterpret_cast<const double2*>(tile + (size_t)jj * S + 2 * rp);
 #pragma unroll
-              for (int k = 0; k < KT; ++k) {
-                const double c = dts[jj * KT + k];
-                la[pp][0][k] = fma(x.x, c, la[pp][0][k]);
-                la[pp][1][k] = fma(x.y, c, la[pp][1][k]);
+                for (int k = 0; k < KT; ++k) {
+                  const double c = dtb[jj * KT + k];
+                  la[pp][0][k] = fma(x.x, c, la[pp][0][k]);
+                  la[pp][1][k] = fma(x.y, c, la[pp][1][k]);
+                }
               }
             }
           }
         }
-      }
-    }
-    if (s == L) break;
+        if (!resident) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[stage]);
+        }
+      };
 
-    // ---- publish this block's lv partial
-    if (cta < gact) {
+      for (int ti = 0; ti < ntile; ++ti, ++tc, ++q) {
+        const int64_t qq = resident ? ti : q;
+        const int stage = (int)(qq % NS);
+        if (!resident || s == 0) mbar_wait(&full[stage], (uint32_t)((qq / NS) & 1));
+        const double* tile = ring + (size_t)stage * TT * S;
+        const int ncol = min(TT, c1 - (c0 + ti * TT));
+        // ---- gradient phase
+        double acc[KT];
 #pragma unroll
-      for (int pp = 0; pp < kNlpMax; ++pp) {
-        const int rp = tid + kFT * pp;
-        if (pp < fg.nlp && rp < npairs) {
+        for (int k = 0; k < KT; ++k) acc[k] = 0;
+        if (gj < ncol) {
+          const double* xc = tile + (size_t)gj * S;
 #pragma unroll
-          for (int k = 0; k < KT; ++k) {
-            double* o = b.lvpart + ((int64_t)cta * KT + k) * n_s + 2 * rp;
-            *reinterpret_cast<double2*>(o) = make_double2(la[pp][0][k], la[pp][1][k]);
+          for (int m = 0; m < NRPM; ++m) {
+            const int rp = grs + RS * (w + kCW * m);
+            if (m < fg.nrp && rp < npairs) {
+              double2 x = *reinterpret_cast<const double2*>(xc + 2 * rp);
+              if (2 * rp + 1 >= n) x.y = 0;
+#pragma unroll
+              for (int k = 0; k < KT; ++k) acc[k] = fma(x.x, Rg[m][0][k], fma(x.y, Rg[m][1][k], acc[k]));
+            }
+          }
+        }
+#pragma unroll
+        for (int o = TT; o < 32; o <<= 1)
+#pragma unroll
+          for (int k = 0; k < KT; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+        const int bsel = (int)(tc & 1);
+        if (lane < TT) {
+          double* gwb = gw + ((size_t)bsel * kCW + w) * TT * KT;
+#pragma unroll
+          for (int k = 0; k < KT; ++k) gwb[lane * KT + k] = acc[k];
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&gdone[bsel]);
+        // ---- lv phase of the previous tile
+        if (ti > 0) lv_phase(ti - 1, tc - 1, q - 1);
+      }
+      if (ntile > 0) lv_phase(ntile - 1, tc - 1, q - 1);
+      if (s == L) break;
+
+      // ---- publish this block's lv partial
+      if (cta < gact) {
+#pragma unroll
+        for (int pp = 0; pp < kNlpMax; ++pp) {
+          const int rp = ct + kCT * pp;
+          if (pp < fg.nlp && rp < npairs) {
+#pragma unroll
+            for (int k = 0; k < KT; ++k) {
+              double* o = b.lvpart + ((int64_t)cta * KT + k) * n_s + 2 * rp;
+              *reinterpret_cast<double2*>(o) = make_double2(la[pp][0][k], la[pp][1][k]);
+            }
           }
         }
       }
-    }
-    grid.sync();
+      grid_barrier(gcounter, gen, G);
 
-    // ---- reduce the partials in block order, softmax, residual, log-likelihood (rows split over all blocks)
-    {
-      const int row0 = cta * fg.rpc, nrows = max(0, min(n, row0 + fg.rpc) - row0);
-      for (int item = w; item < nrows * KT; item += kFW) {
-        const int ii = item / KT, k = item - ii * KT;
-        const double* src = b.lvpart + (int64_t)k * n_s + row0 + ii;
-        double a = 0;
-        for (int sl = lane; sl < gact; sl += 32) a += __ldcg(src + (int64_t)sl * KT * n_s);
-        a = warp_sum(a);
-        if (lane == 0) dl[ii * KT + k] = b.lv_fix[(int64_t)k * n_s + row0 + ii] + a;
-      }
-      __syncthreads();
-      double ll = 0;
-      if (tid < nrows) {
-        const int i = row0 + tid;
-        double l[KT];
-        double m = 0.0;
+      // ---- reduce the partials in block order, softmax, residual, log-likelihood (rows split over all blocks)
+      {
+        const int row0 = cta * fg.rpc, nrows = max(0, min(n, row0 + fg.rpc) - row0);
+        for (int item = w; item < nrows * KT; item += kCW) {
+          const int ii = item / KT, k = item - ii * KT;
+          const double* src = b.lvpart + (int64_t)k * n_s + row0 + ii;
+          double a = 0;
+          for (int sl = lane; sl < gact; sl += 32) a += __ldcg(src + (int64_t)sl * KT * n_s);
+          a = warp_sum(a);
+          if (lane == 0) dl[ii * KT + k] = b.lv_fix[(int64_t)k * n_s + row0 + ii] + a;
+        }
+        named_bar(2, kCT);
+        double ll = 0;
+        if (ct < nrows) {
+          const int i = row0 + ct;
+          double l[KT];
+          double m = 0.0;
 #pragma unroll
-        for (int k = 0; k < KT; ++k) { l[k] = dl[tid * KT + k]; m = fmax(m, l[k]); }
-        double se = exp(0.0 - m);
+          for (int k = 0; k < KT; ++k) { l[k] = dl[ct * KT + k]; m = fmax(m, l[k]); }
+          double se = exp(0.0 - m);
 #pragma unroll
-        for (int k = 0; k < KT; ++k) se += exp(l[k] - m);
-        const double lse = log(se) + m;
-        const int yb = b.ybase[i];
-        if (yb == 0) ll = 0.0 - lse;
+          for (int k = 0; k < KT; ++k) se += exp(l[k] - m);
+          const double lse = log(se) + m;
+          const int yb = b.ybase[i];
+          if (yb == 0) ll = 0.0 - lse;
 #pragma unroll
-        for (int k = 0; k < KT; ++k) {
-          const double nl = l[k] - lse;
-          if (yb == k + 1) ll = nl;
-          b.lv[(int64_t)k * n_s + i] = l[k];
-          b.R[(int64_t)k * n_s + i] = exp(nl) - b.ymat[(int64_t)k * n_s + i];
+          for (int k = 0; k < KT; ++k) {
+            const double nl = l[k] - lse;
+            if (yb == k + 1) ll = nl;
+            b.lv[(int64_t)k * n_s + i] = l[k];
+            b.R[(int64_t)k * n_s + i] = exp(nl) - b.ymat[(int64_t)k * n_s + i];
+          }
+        }
+        ll = warp_sum(ll);
+        if (lane == 0) redsm[w] = ll;
+        named_bar(2, kCT);
+        if (ct == 0) {
+          double t = 0;
+          for (int i = 0; i < kCW; ++i) t += redsm[i];
+          b.red[cta].c = t;
         }
       }
-      ll = block_sum(ll, redsm);
-      if (tid == 0) b.red[cta].c = ll;
+      grid_barrier(gcounter, gen, G);
     }
-    grid.sync();
   }
 
-  if (cta == 0 && tid == 0) {
+  // every block has passed the last grid barrier, so all log-likelihood partials are visible
+  if (cta == 0 && tid == 64) {
     double A = 0;
-    for (int c = 0; c < G; ++c) A += __ldcg(&b.red[c].c);
+    for (unsigned c = 0; c < G; ++c) A += __ldcg(&b.red[c].c);
     ctl->loglike_new = A;
   }
 }
@@ -358,9 +467,10 @@ bool fused_plan(const Geom& g, int smem_optin_bytes, FusedGeom* out) {
   const int n = g.n, K = g.K;
   if (K < 1 || K > 4) return false;
   const int npairs = (n + 1) / 2;
-  if (npairs > kFT * kNlpMax) return false;
-  const int nrpm = K <= 2 ? 8 : 4;
+  if (npairs > kCT * kNlpMax) return false;
+  const int nrpm = 4;
   const int rpc = (n + g.sm_count - 1) / g.sm_count;
+  if (rpc > kCT) return false;
   for (int T = 32; T >= 1; T >>= 1) {
     const int RS = 32 / T;
     // half-stride h = S/2 (in 16-byte chunks) must spread 8 consecutive lanes over 8 distinct bank groups
@@ -370,15 +480,23 @@ bool fused_plan(const Geom& g, int smem_optin_bytes, FusedGeom* out) {
     else if (T == 2) { while (h % 8 != 4) ++h; }
     const int S = 2 * h;
     const size_t tile_bytes = (size_t)T * S * sizeof(double);
-    const size_t other = (size_t)(kFW * T * K + T * K + 32 + rpc * K) * sizeof(double) + 8 * sizeof(uint64_t) + 256;
+    // worst case (every feature in the restricted set): tiles per block, rounded up, times T columns
+    const int tiles_all = (g.nvar + T - 1) / T;
+    const int ncmax = ((tiles_all + g.sm_count - 1) / g.sm_count) * T;
+    const size_t other = (size_t)(2 * kCW * T * K + 2 * T * K + kCW + rpc * K) * sizeof(double) +
+                         (size_t)ncmax * ((2 * K + 2) * sizeof(double) + sizeof(int)) +
+                         (2 * 8 + 4) * sizeof(uint64_t) + 256;
+    if (other > 96 * 1024) continue;
     if (tile_bytes > (T == 1 ? 100 * 1024 : 48 * 1024)) continue;
-    const int nrp = (npairs + RS * kFW - 1) / (RS * kFW);
+    const int nrp = (npairs + RS * kCW - 1) / (RS * kCW);
     if (nrp > nrpm) continue;
+    if ((size_t)smem_optin_bytes < other + 1024 + 2 * tile_bytes) continue;
     const size_t budget = (size_t)smem_optin_bytes - other - 1024;
     int NS = (int)std::min<size_t>(8, budget / tile_bytes);
     if (NS < 2) continue;
-    out->T = T; out->S = S; out->NS = NS; out->nrp = nrp; out->nlp = (npairs + kFT - 1) / kFT; out->rpc = rpc;
+    out->T = T; out->S = S; out->NS = NS; out->nrp = nrp; out->nlp = (npairs + kCT - 1) / kCT; out->rpc = rpc;
     out->grid = g.sm_count;
+    out->ncmax = ncmax;
     out->smem_bytes = (size_t)NS * tile_bytes + other;
     out->smem_bytes_max = (size_t)smem_optin_bytes;
     return true;

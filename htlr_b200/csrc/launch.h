@@ -36,6 +36,7 @@ struct FusedGeom {
   int nlp;     // row pairs per thread, lv phase
   int rpc;     // rows per block in the softmax phase
   int grid;    // blocks (= SMs)
+  int ncmax;   // most restricted-set columns one block can own (state kept in shared memory)
   size_t smem_bytes, smem_bytes_max;
 };
 

@@ -147,6 +147,7 @@ __global__ void __launch_bounds__(256) k_begin(Geom g, Bufs b) {
       for (unsigned i = 0; i < gridDim.x; ++i) { A += b.red[i].a; B += b.red[i].b; }
       ctl->nenergy_old = ctl->loglike - A / 2 - B / 2;
       ctl->loglike_old = ctl->loglike;
+      ctl->ticket[4] = 0;  // grid-barrier counter of the fused trajectory kernel
     }
   }
 }
