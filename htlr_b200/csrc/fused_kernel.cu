@@ -166,6 +166,8 @@ __global__ void __launch_bounds__(kFT, 1) k_traj_fused(Geom g, Bufs b, FusedGeom
   if (warp == 0) {
     // ================================ producer ================================
     int64_t issued = 0;
+    int stage = 0, ti = 0;
+    uint32_t eph = 1;  // parity to wait for on empty[stage]; flips each time the ring wraps (first lap: no wait)
     for (int s = 0; s <= L; ++s) {
       int64_t limit;
       if (resident) limit = ntile;
@@ -174,9 +176,7 @@ __global__ void __launch_bounds__(kFT, 1) k_traj_fused(Geom g, Bufs b, FusedGeom
         if (limit > total_loads) limit = total_loads;
       }
       for (; issued < limit; ++issued) {
-        const int64_t q = issued;
-        const int ti = (int)(q % ntile), stage = (int)(q % NS);
-        if (q >= NS) mbar_wait(&empty[stage], (uint32_t)(((q / NS) - 1) & 1));
+        if (issued >= NS) mbar_wait(&empty[stage], eph);
         const int r0 = c0 + ti * TT;
         const int ncol = min(TT, c1 - r0);
         if (lane == 0) mbar_expect_tx(&full[stage], col_bytes * (uint32_t)ncol);
@@ -185,6 +185,8 @@ __global__ void __launch_bounds__(kFT, 1) k_traj_fused(Geom g, Bufs b, FusedGeom
           const int j = cidx[r0 - c0 + lane];
           bulk_g2s(ring + ((size_t)stage * TT + lane) * S, b.X + (int64_t)j * g.ld, col_bytes, &full[stage]);
         }
+        if (++ti == ntile) ti = 0;
+        if (++stage == NS) { stage = 0; eph ^= 1; }
       }
       if (s < L) { grid_barrier(gcounter, gen, G); grid_barrier(gcounter, gen, G); }
     }
@@ -258,9 +260,28 @@ __global__ void __launch_bounds__(kFT, 1) k_traj_fused(Geom g, Bufs b, FusedGeom
     // ================================ compute ================================
     const int ct = tid - 64, w = warp - 2;
     const int gj = lane % TT, grs = lane / TT;
+    const int tile_stride = TT * S;
+    // per-thread constants of the two phases: shared-memory offsets and validity of each row pair
+    int goff[NRPM];
+    bool gval[NRPM];
+#pragma unroll
+    for (int m = 0; m < NRPM; ++m) {
+      const int rp = grs + RS * (w + kCW * m);
+      gval[m] = (m < fg.nrp) && (rp < npairs);
+      goff[m] = gj * S + 2 * rp;
+    }
+    int loff[kNlpMax];
+    bool lval[kNlpMax];
+#pragma unroll
+    for (int pp = 0; pp < kNlpMax; ++pp) {
+      const int rp = ct + kCT * pp;
+      lval[pp] = (pp < fg.nlp) && (rp < npairs);
+      loff[pp] = 2 * rp;
+    }
     double Rg[NRPM][2][KT];
-    int64_t tc = 0;   // tile counter (gdone / pdone parity), same sequence as the post warp's
-    int64_t q = 0;    // ring position counter
+    int tc = 0;               // tile counter (gdone / pdone parity), same sequence as the post warp's
+    int stage = 0;            // ring position of the tile whose gradient phase runs next
+    uint32_t fph = 0;         // parity to wait for on full[stage]
     for (int s = 0; s <= L; ++s) {
       // residual rows of this thread into registers (published by the previous softmax phase)
 #pragma unroll
@@ -269,10 +290,10 @@ __global__ void __launch_bounds__(kFT, 1) k_traj_fused(Geom g, Bufs b, FusedGeom
 #pragma unroll
         for (int k = 0; k < KT; ++k) {
           double r0v = 0, r1v = 0;
-          if (m < fg.nrp && rp < npairs) {
+          if (gval[m]) {
             const double* Rk = b.R + (int64_t)k * n_s + 2 * rp;
             r0v = __ldcg(Rk);
-            r1v = (2 * rp + 1 < n) ? __ldcg(Rk + 1) : 0.0;
+            r1v = (2 * rp + 1 < n) ? __ldcg(Rk + 1) : 0.0;   // pad row of an odd n contributes nothing
           }
           Rg[m][0][k] = r0v;
           Rg[m][1][k] = r1v;
@@ -283,27 +304,29 @@ __global__ void __launch_bounds__(kFT, 1) k_traj_fused(Geom g, Bufs b, FusedGeom
       for (int pp = 0; pp < kNlpMax; ++pp)
 #pragma unroll
         for (int k = 0; k < KT; ++k) { la[pp][0][k] = 0; la[pp][1][k] = 0; }
+      if (resident) { stage = 0; }
 
       // lv phase of one tile (runs one tile behind the gradient phase)
-      auto lv_phase = [&](int ti_prev, int64_t tc_prev, int64_t q_prev) {
-        const int bsel = (int)(tc_prev & 1);
+      auto lv_phase = [&](int ti_prev, int tc_prev, int stage_prev) {
+        const int bsel = tc_prev & 1;
         mbar_wait(&pdone[bsel], (uint32_t)((tc_prev >> 1) & 1));
-        const int stage = (int)((resident ? ti_prev : q_prev) % NS);
         if (s < L) {
-          const double* tile = ring + (size_t)stage * TT * S;
+          const double* tile = ring + (size_t)stage_prev * tile_stride;
           const double* dtb = dts + bsel * TT * KT;
           const int ncol = min(TT, c1 - (c0 + ti_prev * TT));
 #pragma unroll
           for (int pp = 0; pp < kNlpMax; ++pp) {
-            const int rp = ct + kCT * pp;
-            if (pp < fg.nlp && rp < npairs) {
-              for (int jj = 0; jj < ncol; ++jj) {
-                const double2 x = *reinterpret_cast<const double2*>(tile + (size_t)jj * S + 2 * rp);
+            if (lval[pp]) {
 #pragma unroll
-                for (int k = 0; k < KT; ++k) {
-                  const double c = dtb[jj * KT + k];
-                  la[pp][0][k] = fma(x.x, c, la[pp][0][k]);
-                  la[pp][1][k] = fma(x.y, c, la[pp][1][k]);
+              for (int jj = 0; jj < TT; ++jj) {
+                if (jj < ncol) {
+                  const double2 x = *reinterpret_cast<const double2*>(tile + jj * S + loff[pp]);
+#pragma unroll
+                  for (int k = 0; k < KT; ++k) {
+                    const double c = dtb[jj * KT + k];
+                    la[pp][0][k] = fma(x.x, c, la[pp][0][k]);
+                    la[pp][1][k] = fma(x.y, c, la[pp][1][k]);
+                  }
                 }
               }
             }
@@ -311,28 +334,24 @@ __global__ void __launch_bounds__(kFT, 1) k_traj_fused(Geom g, Bufs b, FusedGeom
         }
         if (!resident) {
           __syncwarp();
-          if (lane == 0) mbar_arrive(&empty[stage]);
+          if (lane == 0) mbar_arrive(&empty[stage_prev]);
         }
       };
 
-      for (int ti = 0; ti < ntile; ++ti, ++tc, ++q) {
-        const int64_t qq = resident ? ti : q;
-        const int stage = (int)(qq % NS);
-        if (!resident || s == 0) mbar_wait(&full[stage], (uint32_t)((qq / NS) & 1));
-        const double* tile = ring + (size_t)stage * TT * S;
+      int stage_prev = 0;
+      for (int ti = 0; ti < ntile; ++ti, ++tc) {
+        if (!resident || s == 0) mbar_wait(&full[stage], fph);
+        const double* tile = ring + (size_t)stage * tile_stride;
         const int ncol = min(TT, c1 - (c0 + ti * TT));
         // ---- gradient phase
         double acc[KT];
 #pragma unroll
         for (int k = 0; k < KT; ++k) acc[k] = 0;
         if (gj < ncol) {
-          const double* xc = tile + (size_t)gj * S;
 #pragma unroll
           for (int m = 0; m < NRPM; ++m) {
-            const int rp = grs + RS * (w + kCW * m);
-            if (m < fg.nrp && rp < npairs) {
-              double2 x = *reinterpret_cast<const double2*>(xc + 2 * rp);
-              if (2 * rp + 1 >= n) x.y = 0;
+            if (gval[m]) {
+              const double2 x = *reinterpret_cast<const double2*>(tile + goff[m]);
 #pragma unroll
               for (int k = 0; k < KT; ++k) acc[k] = fma(x.x, Rg[m][0][k], fma(x.y, Rg[m][1][k], acc[k]));
             }
@@ -342,7 +361,7 @@ __global__ void __launch_bounds__(kFT, 1) k_traj_fused(Geom g, Bufs b, FusedGeom
         for (int o = TT; o < 32; o <<= 1)
 #pragma unroll
           for (int k = 0; k < KT; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
-        const int bsel = (int)(tc & 1);
+        const int bsel = tc & 1;
         if (lane < TT) {
           double* gwb = gw + ((size_t)bsel * kCW + w) * TT * KT;
 #pragma unroll
@@ -351,9 +370,11 @@ __global__ void __launch_bounds__(kFT, 1) k_traj_fused(Geom g, Bufs b, FusedGeom
         __syncwarp();
         if (lane == 0) mbar_arrive(&gdone[bsel]);
         // ---- lv phase of the previous tile
-        if (ti > 0) lv_phase(ti - 1, tc - 1, q - 1);
+        if (ti > 0) lv_phase(ti - 1, tc - 1, stage_prev);
+        stage_prev = stage;
+        if (++stage == NS) { stage = 0; fph ^= 1; }
       }
-      if (ntile > 0) lv_phase(ntile - 1, tc - 1, q - 1);
+      if (ntile > 0) lv_phase(ntile - 1, tc - 1, stage_prev);
       if (s == L) break;
 
       // ---- publish this block's lv partial
