@@ -307,6 +307,8 @@ def main():
                      "hmc_reject": r2["rej"], "gpu_launches": r2["launches"],
                      "kernel_time_share": (r2["prof"]["total_ms"] / r2["prof_steps"]) / (r2["ms"] / max(a.steps, 200))
                      if r2["prof_steps"] else None,
+                     "fused_phase_ms_per_launch_block0": {k: r2["prof"][k] / max(r2["prof_steps"], 1) for k in
+                                                          ("fused_sweep_ms", "fused_barrier_ms", "fused_rowphase_ms")},
                      "note": "restricted regime: X[:,iup] is L2-resident, bound by launch/sync latency not HBM"}
     if dist is not None:
         dist.barrier()
@@ -342,6 +344,8 @@ def main():
                          "kernel": "k_lv_sweep + k_grad_sweep (X sweeps)" if a.algo == 1 else "k_traj_fused (L+1 X sweeps per launch) + detach sweep", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": pr["sweep_bytes"] / max(pr["sweep_launches"], 1),
                          "launches_timed": pr["sweep_launches"], "frac_of_nominal_8TBs": (ach / 8000.0) if ach else None,
+                         "fused_phase_ms_per_launch_block0": {k: pr[k] / max(res["prof_steps"], 1) for k in
+                                                              ("fused_sweep_ms", "fused_barrier_ms", "fused_rowphase_ms")},
                          "iteration_level": {"bytes_two_sweep": bytes_two, "bytes_min_one_sweep": bytes_min,
                                              "achieved_two_sweep_GBs": bytes_two * it_s_1gpu / 1e9,
                                              "frac_two_sweep": bytes_two * it_s_1gpu / 1e9 / peak}},

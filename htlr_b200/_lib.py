@@ -50,7 +50,8 @@ class HtlrProfile(ctypes.Structure):
     _fields_ = [("sweep_ms", ctypes.c_double), ("sweep_bytes", ctypes.c_double),
                 ("sweep_launches", ctypes.c_int64), ("total_ms", ctypes.c_double),
                 ("kernel_launches", ctypes.c_int64), ("sigma_ms", ctypes.c_double),
-                ("reserved", ctypes.c_double * 4)]
+                ("fused_sweep_ms", ctypes.c_double), ("fused_barrier_ms", ctypes.c_double),
+                ("fused_rowphase_ms", ctypes.c_double), ("reserved", ctypes.c_double * 1)]
 
 
 TICK_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(HtlrIterStats),

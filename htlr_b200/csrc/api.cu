@@ -79,6 +79,7 @@ struct htlr_handle {
   double *inj[4] = {nullptr, nullptr, nullptr, nullptr};
   int64_t inj_cap[4] = {0, 0, 0, 0};
   unsigned long long cols_base = 0;  // Ctl::cols_swept at the last profile reset
+  unsigned long long ph_base[4] = {0, 0, 0, 0};
 
   template <class T>
   T* dalloc(size_t count, bool zero = true) {
@@ -782,12 +783,27 @@ int htlr_cuda_profile_get(htlr_handle* h, htlr_profile* out, int32_t reset) {
     CU(cudaMemcpy(&c, h->b.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost));
     h->prof.kernel_launches = h->launches;
     h->prof.sweep_bytes = 8.0 * h->g.n * (double)(c.cols_swept - h->cols_base);
+    int khz = 0;
+    CU(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->cfg.device));
+    const double per_ms = khz > 0 ? (double)khz : 1.0;  // cycles per millisecond at the boost clock
+    h->prof.fused_sweep_ms = (double)(c.ph_cycles[0] - h->ph_base[0]) / per_ms;
+    h->prof.fused_barrier_ms = (double)(c.ph_cycles[1] - h->ph_base[1] + c.ph_cycles[3] - h->ph_base[3]) / per_ms;
+    h->prof.fused_rowphase_ms = (double)(c.ph_cycles[2] - h->ph_base[2]) / per_ms;
     *out = h->prof;
     if (reset) {
       h->prof = htlr_profile{};
       h->cols_base = c.cols_swept;
+      for (int q = 0; q < 4; ++q) h->ph_base[q] = c.ph_cycles[q];
     }
   });
+}
+
+int htlr_cuda_debug_cycles(htlr_handle* h, unsigned long long* out) {
+  Ctl c;
+  cudaStreamSynchronize(h->st);
+  cudaMemcpy(&c, h->b.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost);
+  for (int q = 0; q < 16; ++q) out[q] = c.ph_dbg[q];
+  return 0;
 }
 
 int64_t htlr_cuda_launch_count(const htlr_handle* h) { return h ? h->launches : 0; }

@@ -44,6 +44,10 @@ struct Ctl {
   int err, err_detail;
   // X columns swept so far (lv + gradient sweeps), for the roofline arithmetic
   unsigned long long cols_swept;
+  // fused trajectory kernel, block 0: SM cycles spent in the column sweep, the two grid barriers and the
+  // row phase (partial reduction + softmax), accumulated over launches (htlr_profile.fused_*_ms)
+  unsigned long long ph_cycles[4];
+  unsigned long long ph_dbg[16];
   // scratch counters for "last block finishes" reductions
   unsigned int ticket[8];
 };

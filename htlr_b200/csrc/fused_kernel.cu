@@ -40,6 +40,7 @@ constexpr int kCW = 16;                 // compute warps
 constexpr int kCT = kCW * 32;           // compute threads
 constexpr int kFT = kCT + 64;           // + producer warp + post warp
 constexpr int kNlpMax = 2;              // row pairs per compute thread in the lv phase (n <= 2048)
+constexpr int kPartSlots = 5;           // lv partials one lane sums in the row phase: grids of up to 160 blocks
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -279,10 +280,30 @@ __global__ void __launch_bounds__(kFT, 1) k_traj_fused(Geom g, Bufs b, FusedGeom
       loff[pp] = 2 * rp;
     }
     double Rg[NRPM][2][KT];
+    // row phase: this thread's row of the block's row slice; its fixed part, label and one-hot row never
+    // change during a trajectory, so they are read once
+    const int row0 = cta * fg.rpc, nrows = max(0, min(n, row0 + fg.rpc) - row0);
+    double row_fix[KT], row_y[KT];
+    int row_yb = -1;
+#pragma unroll
+    for (int k = 0; k < KT; ++k) { row_fix[k] = 0; row_y[k] = 0; }
+    if (ct < nrows) {
+      row_yb = b.ybase[row0 + ct];
+#pragma unroll
+      for (int k = 0; k < KT; ++k) {
+        row_fix[k] = b.lv_fix[(int64_t)k * n_s + row0 + ct];
+        row_y[k] = b.ymat[(int64_t)k * n_s + row0 + ct];
+      }
+    }
+    const bool timer = (cta == 0 && tid == 64);
+    const bool timer2 = (cta == 100 && tid == 64);
+    long long dbg[8] = {0,0,0,0,0,0,0,0}, td = 0;
+    long long tk0 = 0, cyc_sweep = 0, cyc_b1 = 0, cyc_row = 0, cyc_b2 = 0;
     int tc = 0;               // tile counter (gdone / pdone parity), same sequence as the post warp's
     int stage = 0;            // ring position of the tile whose gradient phase runs next
     uint32_t fph = 0;         // parity to wait for on full[stage]
     for (int s = 0; s <= L; ++s) {
+      if (timer) tk0 = clock64();
       // residual rows of this thread into registers (published by the previous softmax phase)
 #pragma unroll
       for (int m = 0; m < NRPM; ++m) {
@@ -375,6 +396,7 @@ __global__ void __launch_bounds__(kFT, 1) k_traj_fused(Geom g, Bufs b, FusedGeom
         if (++stage == NS) { stage = 0; fph ^= 1; }
       }
       if (ntile > 0) lv_phase(ntile - 1, tc - 1, stage_prev);
+      if (timer) { const long long t = clock64(); cyc_sweep += t - tk0; tk0 = t; }
       if (s == L) break;
 
       // ---- publish this block's lv partial
@@ -392,50 +414,73 @@ __global__ void __launch_bounds__(kFT, 1) k_traj_fused(Geom g, Bufs b, FusedGeom
         }
       }
       grid_barrier(gcounter, gen, G);
+      if (timer) { const long long t = clock64(); cyc_b1 += t - tk0; tk0 = t; }
+      if (timer || timer2) td = clock64();
 
       // ---- reduce the partials in block order, softmax, residual, log-likelihood (rows split over all blocks)
       {
-        const int row0 = cta * fg.rpc, nrows = max(0, min(n, row0 + fg.rpc) - row0);
+        // one (row, class) item per warp pass; all of a lane's partials are requested before any is summed,
+        // so the pass costs one L2 round trip instead of one per 32 blocks
         for (int item = w; item < nrows * KT; item += kCW) {
           const int ii = item / KT, k = item - ii * KT;
           const double* src = b.lvpart + (int64_t)k * n_s + row0 + ii;
-          double a = 0;
-          for (int sl = lane; sl < gact; sl += 32) a += __ldcg(src + (int64_t)sl * KT * n_s);
+          double pv[kPartSlots];
+#pragma unroll
+          for (int q = 0; q < kPartSlots; ++q) {
+            const int sl = lane + 32 * q;
+            pv[q] = (sl < gact) ? __ldcg(src + (int64_t)sl * KT * n_s) : 0.0;
+          }
+          double a = pv[0];
+#pragma unroll
+          for (int q = 1; q < kPartSlots; ++q) a += pv[q];
           a = warp_sum(a);
-          if (lane == 0) dl[ii * KT + k] = b.lv_fix[(int64_t)k * n_s + row0 + ii] + a;
+          if (lane == 0) dl[ii * KT + k] = a;
         }
+        if (timer || timer2) { const long long t = clock64(); dbg[0] += t - td; td = t; }
         named_bar(2, kCT);
+        if (timer || timer2) { const long long t = clock64(); dbg[1] += t - td; td = t; }
         double ll = 0;
         if (ct < nrows) {
           const int i = row0 + ct;
           double l[KT];
           double m = 0.0;
 #pragma unroll
-          for (int k = 0; k < KT; ++k) { l[k] = dl[ct * KT + k]; m = fmax(m, l[k]); }
+          for (int k = 0; k < KT; ++k) { l[k] = row_fix[k] + dl[ct * KT + k]; m = fmax(m, l[k]); }
           double se = exp(0.0 - m);
 #pragma unroll
           for (int k = 0; k < KT; ++k) se += exp(l[k] - m);
           const double lse = log(se) + m;
-          const int yb = b.ybase[i];
-          if (yb == 0) ll = 0.0 - lse;
+          if (row_yb == 0) ll = 0.0 - lse;
 #pragma unroll
           for (int k = 0; k < KT; ++k) {
             const double nl = l[k] - lse;
-            if (yb == k + 1) ll = nl;
+            if (row_yb == k + 1) ll = nl;
             b.lv[(int64_t)k * n_s + i] = l[k];
-            b.R[(int64_t)k * n_s + i] = exp(nl) - b.ymat[(int64_t)k * n_s + i];
+            __stcg(&b.R[(int64_t)k * n_s + i], exp(nl) - row_y[k]);
           }
         }
         ll = warp_sum(ll);
+        if (timer || timer2) { const long long t = clock64(); dbg[2] += t - td; td = t; }
         if (lane == 0) redsm[w] = ll;
         named_bar(2, kCT);
+        if (timer || timer2) { const long long t = clock64(); dbg[3] += t - td; td = t; }
         if (ct == 0) {
           double t = 0;
           for (int i = 0; i < kCW; ++i) t += redsm[i];
           b.red[cta].c = t;
         }
       }
+      if (timer) { const long long t = clock64(); cyc_row += t - tk0; tk0 = t; }
       grid_barrier(gcounter, gen, G);
+      if (timer) { const long long t = clock64(); cyc_b2 += t - tk0; }
+      if (timer || timer2) { const long long t = clock64(); dbg[4] += t - td; td = t; }
+    }
+    if (timer || timer2) for (int q = 0; q < 8; ++q) ctl->ph_dbg[q + (timer2 ? 8 : 0)] += (unsigned long long)dbg[q];
+    if (timer) {
+      ctl->ph_cycles[0] += (unsigned long long)cyc_sweep;
+      ctl->ph_cycles[1] += (unsigned long long)cyc_b1;
+      ctl->ph_cycles[2] += (unsigned long long)cyc_row;
+      ctl->ph_cycles[3] += (unsigned long long)cyc_b2;
     }
   }
 
@@ -492,6 +537,7 @@ bool fused_plan(const Geom& g, int smem_optin_bytes, FusedGeom* out) {
   const int nrpm = 4;
   const int rpc = (n + g.sm_count - 1) / g.sm_count;
   if (rpc > kCT) return false;
+  if (g.sm_count > 32 * kPartSlots) return false;   // row phase: one lane sums at most kPartSlots block partials
   for (int T = 32; T >= 1; T >>= 1) {
     const int RS = 32 / T;
     // half-stride h = S/2 (in 16-byte chunks) must spread 8 consecutive lanes over 8 distinct bank groups

@@ -103,7 +103,10 @@ typedef struct htlr_profile {
   double total_ms;        /* all kernels of the timed thin-steps */
   int64_t kernel_launches;/* launches issued by this library since create / reset */
   double sigma_ms;        /* per-feature variance update (gamma draws or warp-per-feature ARS) */
-  double reserved[4];
+  /* fused trajectory kernel, block 0's view (SM cycle counter / clock rate): time in the column sweeps,
+   * waiting at the two grid-wide barriers of each leapfrog step, and in the row phase between them */
+  double fused_sweep_ms, fused_barrier_ms, fused_rowphase_ms;
+  double reserved[1];
 } htlr_profile;
 
 /* Replaces `Fit::Fit` + `Fit::Initialize` (gibbs.cpp:4-50, 519-530).

@@ -1,0 +1,116 @@
+"""The stand-alone C++ host (htlr_b200/host/fit_host: cuda_fit.hpp above the C ABI, what the Rcpp glue does
+without R) against the ctypes mirror and the CPU oracle."""
+import os
+import struct
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from tests.helpers import problem, relerr, streams
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "htlr_b200", "host", "fit_host")
+
+
+def write_problem(path, a, device=0, algo=0, seed=0, inject=None, ars_width=0):
+    nvar = a["p"] + 1
+    with open(path, "wb") as f:
+        pt = a["ptype"].encode()
+        f.write(struct.pack("<Iiiii", 0x48544C52, a["p"], a["K"], a["n"], len(pt)) + pt)
+        f.write(struct.pack("<dddiiiiiddiii", a["alpha"], a["s"], a["eta"], a["iters_rmc"], a["iters_h"], a["thin"],
+                            a["leap_L"], a["leap_L_h"], a["leap_step"], a["hmc_sgmcut"], int(a["keep_warmup_hist"]),
+                            int(a["silence"]), int(a["legacy"])))
+        f.write(struct.pack("<iiQii", device, algo, seed, ars_width, 1 if inject else 0))
+        f.write(np.asfortranarray(a["X"], dtype=np.float64).tobytes(order="F"))
+        f.write(np.asfortranarray(np.reshape(a["ymat"], (a["n"], a["K"]), order="F")).tobytes(order="F"))
+        f.write(np.ascontiguousarray(a["ybase"], dtype=np.int64).tobytes())
+        f.write(np.asfortranarray(a["deltas"], dtype=np.float64).tobytes(order="F"))
+        f.write(np.ascontiguousarray(a["sigmasbt"], dtype=np.float64).tobytes())
+        if inject:
+            ars = inject.get("ars_uniforms")
+            f.write(struct.pack("<qqqq", inject["normals"].size, inject["uniforms"].size, inject["gammas"].size,
+                                0 if ars is None else ars.shape[0]))
+            for k in ("normals", "uniforms", "gammas"):
+                f.write(np.ascontiguousarray(inject[k], dtype=np.float64).tobytes())
+            if ars is not None:
+                f.write(np.ascontiguousarray(ars, dtype=np.float64).tobytes())
+    assert nvar > 0
+
+
+def read_result(path, a):
+    nvar, K = a["p"] + 1, a["K"]
+    raw = open(path, "rb").read()
+    H = struct.unpack_from("<i", raw, 0)[0]
+    sg = struct.unpack_from("<d", raw, 4)[0]
+    d = np.frombuffer(raw, dtype=np.float64, offset=12)
+    out, at = {"H": H, "sgmsq.cut": sg}, 0
+    for name, shape in (("DDNloglike", (1, nvar)), ("mcdeltas", (nvar, K, H)), ("mclogw", (H, 1)),
+                        ("mcsigmasbt", (nvar, H)), ("mcvardeltas", (nvar, H)), ("mcloglike", (H, 1)),
+                        ("mcuvar", (H, 1)), ("mchmcrej", (H, 1))):
+        cnt = int(np.prod(shape))
+        out[name] = d[at:at + cnt].reshape(shape, order="F")
+        at += cnt
+    assert at == d.size
+    return out
+
+
+def run_host(a, **kw):
+    with tempfile.TemporaryDirectory() as td:
+        pi, po = os.path.join(td, "problem.bin"), os.path.join(td, "result.bin")
+        write_problem(pi, a, **kw)
+        r = subprocess.run([HOST, pi, po], capture_output=True, text=True, timeout=300)
+        if r.returncode != 0:
+            return r, None
+        return r, read_result(po, a)
+
+
+def test_host_binary_built():
+    assert os.path.exists(HOST), "make -C htlr_b200/csrc builds htlr_b200/host/fit_host"
+
+
+def test_host_fails_loudly_without_gpu_or_with_bad_prior():
+    """No CPU fallback: without a CUDA device the C++ host exits non-zero with the library's message.
+    (On a GPU box the same call succeeds, so only the bad-prior leg is checked there.)"""
+    a = problem(30, 10, 3, seed=2, iters_rmc=2, iters_h=1)
+    r, out = run_host(dict(a, ptype="cauchy"))
+    assert r.returncode == 3 and "Unsupported prior type" in r.stderr and out is None
+    import torch
+    if not torch.cuda.is_available():
+        r, out = run_host(a)
+        assert r.returncode == 3 and "no CUDA device" in r.stderr
+
+
+@pytest.mark.gpu
+def test_host_cpp_chain_matches_oracle_and_ctypes():
+    import htlr_b200
+    from oracle import oracle as O
+    a = problem(90, 70, 3, seed=41, iters_rmc=5, iters_h=4, keep_warmup_hist=True)
+    st = streams(a, seed=6)
+    r, out = run_host(a, inject=st)
+    assert r.returncode == 0, r.stderr
+    ora = O.OracleFit(**a)
+    ora.initialize()
+    ora.set_inject(st["normals"], st["uniforms"], st["gammas"], None)
+    ora.run(9)
+    b = ora.fetch()
+    for k in ("mcdeltas", "mcsigmasbt", "mcvardeltas", "mclogw", "mcloglike", "mcuvar", "mchmcrej"):
+        assert relerr(np.ravel(out[k]), np.ravel(b[k])) < 1e-8, k
+    assert relerr(out["DDNloglike"].ravel(), b["DDNloglike"]) < 1e-12
+    # device RNG: the C++ host and the ctypes mirror give the very same chain for the same key
+    r, out2 = run_host(a, seed=123)
+    assert r.returncode == 0, r.stderr
+    py = htlr_b200.htlr_fit_helper(**a, seed=123)
+    for k in ("mcdeltas", "mcsigmasbt", "mcvardeltas", "mcloglike", "mcuvar", "mchmcrej"):
+        assert np.array_equal(np.ravel(out2[k]), np.ravel(py[k])), k
+
+
+@pytest.mark.gpu
+def test_host_cpp_progress_lines():
+    """silence = 0 prints the reference's progress line (gibbs.cpp:119-121) once per iteration."""
+    a = problem(40, 20, 2, seed=4, iters_rmc=3, iters_h=2, silence=0)
+    r, out = run_host(a, seed=5)
+    assert r.returncode == 0, r.stderr
+    lines = [l for l in r.stdout.splitlines() if l.startswith("Iter")]
+    assert len(lines) == 5 and lines[0].startswith("Iter  -2: deviance=") and "nuvar=" in lines[-1]
