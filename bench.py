@@ -41,7 +41,12 @@ WORKLOADS = {
     "D": dict(gen="mlr", n=200, p=50000, C=2, cut=0.0, seed=1004,
               desc="gendata_MLR n=200 p=50000 C=2, t prior df=1, leap=50, cut=0 (one chain)"),
     "tiny": dict(gen="mlr", n=120, p=400, C=3, cut=0.0, seed=5, desc="tiny smoke workload"),
+    # config E: ONE chain over all ranks, X row-sharded, NCCL all-reduce of the u x K gradient per leapfrog step
+    "E": dict(gen="mlr_device", n=200000, p=10000, C=5, cut=0.0, seed=1005,
+              desc="tall gendata_MLR n=200000 p=10000 C=5 generated on device, t prior df=1, leap=50, cut=0, "
+                   "row-sharded over the ranks with an NCCL all-reduce of the gradient partials"),
 }
+E_CPU_ROWS = 2000   # rows of the CPU-reference sample of workload E (rate scaled by E_CPU_ROWS / n)
 HTLR_DEFAULTS = dict(ptype="t", alpha=1.0, s=-10.0, eta=0.0, thin=1, leap_L=50, leap_L_h=5, leap_step=0.3,
                      keep_warmup_hist=False, silence=1, legacy=False)
 
@@ -49,7 +54,12 @@ HTLR_DEFAULTS = dict(ptype="t", alpha=1.0, s=-10.0, eta=0.0, thin=1, leap_L=50, 
 def make_problem(wl, chain_seed=0):
     from htlr_b200 import synth
     w = WORKLOADS[wl]
-    if w["gen"] == "fam":
+    if w["gen"] == "mlr_device":
+        # CPU legs only: a host-generated row subsample of the same law (the reference's cost is linear in n)
+        w = dict(w, n=E_CPU_ROWS)
+        d = synth.gendata_mlr(w["n"], w["p"], NC=w["C"], seed=w["seed"])
+        d["y"][:w["C"]] = np.arange(w["C"])
+    elif w["gen"] == "fam":
         d = synth.gendata_fam(w["n"], w["p"], sd_g=0.5, stdx=True, seed=w["seed"])
     else:
         d = synth.gendata_mlr(w["n"], w["p"], NC=w["C"], seed=w["seed"])
@@ -164,13 +174,19 @@ def run_reference_arm(a):
     warm = 0 if w["cut"] <= 0 else 150
     rate, kind, m = cpu_reference_rate(a.workload, a.steps, budget_s=150.0, warm_iters=warm)
     cores = os.cpu_count()
+    scale_note = ""
+    if a.workload == "E":
+        n_total = a.n_total or w["n"]
+        rate *= E_CPU_ROWS / n_total
+        scale_note = f"; timed on a {E_CPU_ROWS}-row sample of the same law and scaled linearly to n={n_total}"
     line = {"impl": "reference", "metric": "mcmc_iterations_per_sec", "value": rate, "unit": "it/s",
             "n_gpus": a.gpus, "steps": m, "warmup": warm, "ms_per_step": 1e3 / rate, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": w["desc"], "regime": "full" if w["cut"] <= 0 else "restricted"},
             "cpu_baseline": {"value": rate, "unit": "it/s", "cores": 1, "kind": kind,
                              "sample": f"{m} sampling iterations (L=50) of the same workload, time-boxed to ~150 s; "
-                                       f"single thread of {cores} host cores (the reference's hot loops are single-threaded)"},
+                                       f"single thread of {cores} host cores (the reference's hot loops are single-threaded)"
+                                       + scale_note},
             "e2e": {"value": rate, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -253,6 +269,105 @@ def measure_e2e(torch, wl, steps, device, chain_seed, dist):
     return (t1 - t0), h2d / steps, d2h / steps, warm_iters
 
 
+def make_tall_on_device(torch, n_total, p, C, rank, world, seed):
+    """gendata_MLR law (R/gendata.r:26-46) for this rank's row block, generated on the GPU (16 GB of X at
+    full size never exists on the host). Coefficients come from the common seed, rows from seed + 1 + rank."""
+    from htlr_b200 import shard
+    lo, hi = shard.row_range(n_total, rank, world)
+    nl = hi - lo
+    ld = (nl + 15) // 16 * 16
+    dev = torch.device("cuda", torch.cuda.current_device())
+    gc = torch.Generator(device=dev); gc.manual_seed(seed)
+    gr = torch.Generator(device=dev); gr.manual_seed(seed + 1 + rank)
+    sig = 1.0 / torch.empty(p, dtype=torch.float64, device=dev).exponential_(1.0, generator=gc)   # 1/Gamma(1, 1)
+    betas = torch.randn(p + 1, C, dtype=torch.float64, device=dev, generator=gc)
+    betas *= torch.cat([torch.zeros(1, dtype=torch.float64, device=dev), sig.sqrt()])[:, None]
+    Xt = torch.zeros(p + 1, ld, dtype=torch.float64, device=dev)     # row j = column j of X (column-major n x nvar)
+    Xt[0, :nl] = 1.0
+    lv = betas[0][None, :].repeat(nl, 1)
+    step = max(1, (1 << 27) // ld)
+    for j0 in range(1, p + 1, step):
+        j1 = min(p + 1, j0 + step)
+        blk = torch.randn(j1 - j0, nl, dtype=torch.float64, device=dev, generator=gr)
+        Xt[j0:j1, :nl] = blk
+        lv += blk.T @ betas[j0:j1]          # data generation only (cuBLAS); not part of the measured path
+        del blk
+    # coefficients this heavy-tailed give near-degenerate class probabilities; that is the law, keep it
+    pr = torch.softmax(lv, dim=1)
+    y = torch.multinomial(pr, 1, generator=gr).squeeze(1)
+    if rank == 0:
+        y[:C] = torch.arange(C, device=dev)
+    K = C - 1
+    ymat = (y[None, :] == torch.arange(1, C, device=dev)[:, None]).to(torch.float64).contiguous()   # [k][i]
+    ybase = y.to(torch.int64).contiguous()
+    return dict(Xt=Xt, ld=ld, ymat=ymat, ybase=ybase, n_local=nl, K=K)
+
+
+def measure_tall(torch, a, dist, rank, world, local):
+    """Config E: one chain, rows sharded over the ranks. Strong scaling: total work fixed as N grows."""
+    import htlr_b200
+    from htlr_b200 import shard, synth
+    w = WORKLOADS["E"]
+    n_total = a.n_total or w["n"]
+    p, C = w["p"], w["C"]
+    d = make_tall_on_device(torch, n_total, p, C, rank, world, w["seed"])
+    K, nl = d["K"], d["n_local"]
+    deltas, sig = synth.init_state(p, K, init="zero", seed=w["seed"] + 17)
+    total = a.warmup + a.steps + min(a.steps, 5)
+    comm = None
+    if world > 1:
+        uid = shard.exchange_unique_id(dist, shard.nccl_unique_id)
+        comm = shard.nccl_init(uid, rank, world, local)
+    kw = dict(HTLR_DEFAULTS)
+    smp = htlr_b200.Sampler(p, K, nl, None, None, None, hmc_sgmcut=w["cut"], deltas=deltas, sigmasbt=sig, iters_h=0,
+                            iters_rmc=total, device=local, seed=1000, nccl_comm=comm,
+                            device_ptrs=(d["Xt"].data_ptr(), d["ld"], d["ymat"].data_ptr(), d["ybase"].data_ptr()),
+                            **kw)
+    smp.run(a.warmup)
+    l0 = smp.launch_count
+    ms = time_chain(torch, smp, a.steps, dist)
+    launches = smp.launch_count - l0
+    smp.profile_enable(True)
+    smp.profile_get(reset=True)
+    psteps = min(a.steps, 5)
+    smp.run(psteps)
+    pr = smp.profile_get()
+    smp.profile_enable(False)
+    out = smp.fetch()
+    smp.close()
+    if comm is not None:
+        shard.nccl_destroy(comm)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t[0])
+    if rank != 0:
+        return
+    peak, peak_src = measured_peak()
+    ach = (pr["sweep_bytes"] / 1e9) / (pr["sweep_ms"] * 1e-3)
+    u = float(np.mean(out["mcuvar"][a.warmup + 1:a.warmup + 1 + a.steps]))
+    line = {"metric": "mcmc_iterations_per_sec", "value": a.steps / (ms_max * 1e-3), "unit": "it/s", "n_gpus": world,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_max / a.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": w["desc"] if n_total == w["n"] else w["desc"].replace("n=200000", f"n={n_total}"),
+                       "regime": "full", "rows_per_rank": nl,
+                       "l2": "X shard (%.1f GB) is larger than the 126 MB L2; no flush needed" % (8e-9 * nl * (p + 1)),
+                       "parallelism": f"rows sharded over {world} rank(s), NCCL all-reduce (sum, f64) of the "
+                                      f"{p + 1}x{K} gradient partials + log-likelihood per gradient evaluation"
+                       if world > 1 else "1 GPU holds all rows",
+                       "algorithm": "two-sweep (lv sweep + gradient sweep per leapfrog step)", "mean_nuvar": u,
+                       "hmc_reject": float(np.mean(out["mchmcrej"][a.warmup + 1:a.warmup + 1 + a.steps]))},
+            "e2e": None, "e2e_note": "X is generated on the device (16 GB at full size); the host-buffer end-to-end "
+                                     "number is measured on the default workload",
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "traffic": None, "kernel": "k_lv_sweep + k_grad_sweep over this rank's row block",
+                         "peak_source": peak_src, "launches_timed": pr["sweep_launches"],
+                         "algorithmic_bytes_per_launch": pr["sweep_bytes"] / max(pr["sweep_launches"], 1),
+                         "sweep_share_of_step": pr["sweep_ms"] / max(pr["total_ms"], 1e-9)}}
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -263,8 +378,15 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the default-cut (restricted) block")
     ap.add_argument("--algo", type=int, default=0, help="0 auto (fused when applicable), 1 two-sweep, 2 fused")
+    ap.add_argument("--n-total", type=int, default=0, help="workload E only: total rows (default 200000)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
+    # ONE JSON line on stdout: native libraries (NCCL banner, ...) print to fd 1, so park it on stderr and
+    # keep the real stdout for the result line
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     global ALGO
     ALGO = a.algo
 
@@ -284,6 +406,12 @@ def main():
         import torch.distributed as dist_mod
         dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
         dist = dist_mod
+
+    if a.workload == "E":
+        measure_tall(torch, a, dist, rank, world, local)
+        if dist is not None:
+            dist.destroy_process_group()
+        return
 
     w = WORKLOADS[a.workload]
     clocks = ClockSampler(local)

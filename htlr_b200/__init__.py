@@ -6,4 +6,5 @@ the in-tree C-ABI library `libhtlr_cuda.so` (include/htlr_cuda.h); importing thi
 or calling it without a B200, fails loudly — there is no CPU path.
 """
 from .fit import HtlrCudaError, Sampler, ars_sample, htlr_fit_helper, rng_dump  # noqa: F401
-from . import _lib  # noqa: F401
+from . import _lib, shard  # noqa: F401
+from .shard import ShardedSampler  # noqa: F401

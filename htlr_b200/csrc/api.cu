@@ -59,11 +59,14 @@ struct htlr_handle {
   std::string err;
   int iters_done = 0;  // outer iterations enqueued so far
   std::vector<void*> allocs;
-  std::map<int, cudaGraphExec_t> graphs;
+  std::map<int, cudaGraphExec_t> graphs;   // key: 2 * L + use_cluster
   ncclComm_t comm = nullptr;
   bool sharded = false;
-  bool fused = false;
+  bool fused = false;       // grid-mode fused trajectory kernel applies
   FusedGeom fg{};
+  bool has_cluster = false; // cluster-mode flavour applies (fgc)
+  FusedGeom fgc{};
+  bool use_cluster = false; // launch the cluster-mode flavour ahead of the grid-mode one
   bool profiling = false;
   std::vector<EventPair> ev_pool;
   size_t ev_used = 0;
@@ -173,6 +176,13 @@ int enqueue_step(htlr_handle* h, int L, bool until_energy_only = false) {
   launch_softmax(g, b, 0, nullptr, nullptr, nullptr, nullptr, nullptr, st); ++nk;
   if (h->fused) {
     ProfScope ps(h, 0);
+    h->fg.timing = h->fgc.timing = h->profiling ? 1 : 0;
+    if (h->use_cluster) {
+      // one cluster runs the whole trajectory out of shared memory when the restricted set is small enough
+      // (cl_umax); otherwise it leaves traj_done = 0 and the grid-mode launch does the work
+      CU(launch_traj_fused(g, b, h->fgc, L, st));
+      ++nk;
+    }
     CU(launch_traj_fused(g, b, h->fg, L, st));
     ++nk;
   } else {
@@ -205,7 +215,8 @@ int enqueue_step(htlr_handle* h, int L, bool until_energy_only = false) {
 }
 
 cudaGraphExec_t get_graph(htlr_handle* h, int L) {
-  auto it = h->graphs.find(L);
+  const int key = 2 * L + (h->use_cluster ? 1 : 0);
+  auto it = h->graphs.find(key);
   if (it != h->graphs.end()) return it->second;
   cudaGraph_t graph;
   CU(cudaStreamBeginCapture(h->st, cudaStreamCaptureModeThreadLocal));
@@ -222,7 +233,7 @@ cudaGraphExec_t get_graph(htlr_handle* h, int L) {
   cudaGraphExec_t exec;
   CU(cudaGraphInstantiate(&exec, graph, 0));
   CU(cudaGraphDestroy(graph));
-  h->graphs[L] = exec;
+  h->graphs[key] = exec;
   h->kernels_per_step_cache = nk;
   return exec;
 }
@@ -230,7 +241,7 @@ cudaGraphExec_t get_graph(htlr_handle* h, int L) {
 int kernels_per_step(const htlr_handle* h, int L) {
   int per_grad = h->sharded ? 3 : 2;
   int n = 2 + 2 + per_grad + L * (2 + per_grad) + 1 + 1 + 1 + 1;
-  if (h->fused) n = 2 + 2 + 1 + 1 + 1 + 1 + 1;
+  if (h->fused) n = 2 + 2 + 1 + 1 + 1 + 1 + 1 + (h->use_cluster ? 1 : 0);
   if (h->cfg.ptype == HTLR_PRIOR_T && h->cfg.eta > 1e-10) n += 1;
   return n;
 }
@@ -386,11 +397,28 @@ void do_create(const htlr_cfg* cfg, const double* X, int64_t ldx, const double* 
     FusedGeom fgm{};
     int coop = 0;
     CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c.device));
-    const bool can = coop && !h->sharded && fused_plan(g, (int)prop.sharedMemPerBlockOptin, &fgm);
-    if (c.algo == HTLR_ALGO_FUSED && !can)
+    const bool can = coop && !h->sharded && fused_plan(g, (int)prop.sharedMemPerBlockOptin, 0, &fgm);
+    if ((c.algo == HTLR_ALGO_FUSED || c.algo == HTLR_ALGO_FUSED_CLUSTER) && !can)
       FAIL(HTLR_E_ARG, "fused trajectory not applicable (needs K <= 4, a column tile in shared memory, one GPU)");
     h->fused = can && c.algo != HTLR_ALGO_TWO_SWEEP;
     h->fg = fgm;
+    if (h->fused && c.algo != HTLR_ALGO_FUSED) {
+      const int cl = fused_cluster_size(g, (int)prop.sharedMemPerBlockOptin);
+      h->has_cluster = cl > 0 && fused_plan(g, (int)prop.sharedMemPerBlockOptin, cl, &h->fgc);
+      if (h->has_cluster) {
+        // Which flavour runs is decided on the device, per iteration, from the restricted-set size: both are
+        // launched and the one that is not wanted returns at once (~2.5 us). Grid mode (148 blocks, exchange
+        // through L2) is bandwidth efficient; cluster mode (one cluster, exchange through shared memory,
+        // hardware barriers) has lower latency per leapfrog step but a fraction of the bandwidth: measured
+        // crossover at about 3 MB of X[:, iup] (tools/mode_sweep.py).
+        const int cap = h->fgc.cl * h->fgc.ncmax;
+        const int by_bytes = (int)std::min<double>(3.0e6 / (8.0 * n), 2.0e9);
+        h->fgc.cl_umax = c.algo == HTLR_ALGO_FUSED_CLUSTER ? cap : std::min(cap, by_bytes);
+      }
+    }
+    if (c.algo == HTLR_ALGO_FUSED_CLUSTER && !h->has_cluster)
+      FAIL(HTLR_E_ARG, "cluster-mode trajectory kernel not available on this device");
+    h->use_cluster = h->fused && h->has_cluster;
   }
   b.lvpart = h->dalloc<double>((size_t)std::max(g.lv_cs, g.sm_count) * K * g.n_s);
   b.red = h->dalloc<Red4>((size_t)std::max(std::max(g.e_grid, (n + 255) / 256), g.sm_count));
@@ -796,14 +824,6 @@ int htlr_cuda_profile_get(htlr_handle* h, htlr_profile* out, int32_t reset) {
       for (int q = 0; q < 4; ++q) h->ph_base[q] = c.ph_cycles[q];
     }
   });
-}
-
-int htlr_cuda_debug_cycles(htlr_handle* h, unsigned long long* out) {
-  Ctl c;
-  cudaStreamSynchronize(h->st);
-  cudaMemcpy(&c, h->b.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost);
-  for (int q = 0; q < 16; ++q) out[q] = c.ph_dbg[q];
-  return 0;
 }
 
 int64_t htlr_cuda_launch_count(const htlr_handle* h) { return h ? h->launches : 0; }

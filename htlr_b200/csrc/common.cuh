@@ -36,6 +36,7 @@ struct Ctl {
   double logw, loglike, loglike_new, loglike_old;
   double nenergy_old, nenergy_new;
   int accept;
+  int traj_done;   // cluster-mode trajectory kernel ran this thin-step (the grid-mode launch then exits)
   double uvar_acc, rej_acc;
   // inject cursors and sizes
   long long cur_norm, cur_unif, cur_gam, n_norm, n_unif, n_gam, n_ars_blocks;
@@ -47,7 +48,6 @@ struct Ctl {
   // fused trajectory kernel, block 0: SM cycles spent in the column sweep, the two grid barriers and the
   // row phase (partial reduction + softmax), accumulated over launches (htlr_profile.fused_*_ms)
   unsigned long long ph_cycles[4];
-  unsigned long long ph_dbg[16];
   // scratch counters for "last block finishes" reductions
   unsigned int ticket[8];
 };

@@ -27,16 +27,20 @@ struct Geom {
   int sm_count;
 };
 
-// Tile shape of the fused trajectory kernel (fused_kernel.cu), chosen once per handle by fused_plan().
+// Shape of the fused trajectory kernel (traj_kernel.cu), chosen once per handle by fused_plan().
 struct FusedGeom {
-  int T;       // columns per shared-memory tile
-  int S;       // column stride in shared memory (doubles), even, chosen bank-conflict-free
-  int NS;      // ring stages
-  int nrp;     // row pairs per thread, gradient phase
-  int nlp;     // row pairs per thread, lv phase
+  int T;       // columns per ring stage (1)
+  int S;       // column stride in shared memory (doubles), even
+  int NS;      // ring stages per compute group
+  int nrp;     // row pairs per thread within a column (template parameter: 1, 2 or 4)
+  int gw;      // warps per compute group (template parameter: 1, 4, 8 or 16)
+  int nlp;     // row pairs per thread when publishing the block's lv partial
   int rpc;     // rows per block in the softmax phase
-  int grid;    // blocks (= SMs)
+  int grid;    // blocks (= SMs, or the cluster size)
+  int cl;      // 0: grid mode (cooperative launch); > 0: one thread-block cluster of this many blocks
   int ncmax;   // most restricted-set columns one block can own (state kept in shared memory)
+  int cl_umax; // cluster mode runs the trajectory only while the restricted set has at most this many columns
+  int timing;  // 1: block 0 accumulates per-phase cycle counts into Ctl::ph_cycles (profiling runs only)
   size_t smem_bytes, smem_bytes_max;
 };
 
@@ -92,8 +96,9 @@ void launch_vardeltas_all(const Geom& g, const Bufs& b, cudaStream_t st);
 void launch_scatter_proposal(const Geom& g, const Bufs& b, double* deltas_out, double* momt_out,
                              double* vd_out, cudaStream_t st);
 
-// fused_kernel.cu
-bool fused_plan(const Geom& g, int smem_optin_bytes, FusedGeom* out);
+// traj_kernel.cu
+bool fused_plan(const Geom& g, int smem_optin_bytes, int cl, FusedGeom* out);
+int fused_cluster_size(const Geom& g, int smem_optin_bytes);
 cudaError_t launch_traj_fused(const Geom& g, const Bufs& b, const FusedGeom& fg, int L, cudaStream_t st);
 
 // sigma_kernels.cu (compiled with --fmad=false)

@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(256) k_begin(Geom g, Bufs b) {
       ctl->nenergy_old = ctl->loglike - A / 2 - B / 2;
       ctl->loglike_old = ctl->loglike;
       ctl->ticket[4] = 0;  // grid-barrier counter of the fused trajectory kernel
+      ctl->traj_done = 0;
     }
   }
 }
@@ -586,8 +587,15 @@ void launch_softmax(const Geom& g, const Bufs& b, int what, const int* cnt, doub
 void launch_grad_sweep(const Geom& g, const Bufs& b, const int* idx, const int* cnt, const double* R,
                        double* gout, cudaStream_t st) {
   dim3 grid(g.g_gx, g.g_rt);
-  const size_t smem = (size_t)g.K * g.g_tr * sizeof(double);
-  DISPATCH_K(g.K, k_grad_sweep<KT><<<grid, 256, smem, st>>>(g, b, idx, cnt, R, gout));
+  const size_t smem = (size_t)g.K * g.g_tr * sizeof(double);   // <= 64 KB by the choice of g_tr
+  DISPATCH_K(g.K, {
+    static bool configured = false;   // per instantiation: the residual tile can exceed the 48 KB default
+    if (!configured) {
+      cudaFuncSetAttribute(k_grad_sweep<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+      configured = true;
+    }
+    k_grad_sweep<KT><<<grid, 256, smem, st>>>(g, b, idx, cnt, R, gout);
+  });
 }
 void launch_gsum(const Geom& g, const Bufs& b, const int* cnt, double* gout, cudaStream_t st) {
   k_gsum<<<g.e_grid, 256, 0, st>>>(g, b, cnt, gout);

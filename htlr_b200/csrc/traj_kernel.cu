@@ -1,0 +1,759 @@
+// Fused leapfrog trajectory: ONE persistent kernel runs all L+1 gradient evaluations of an HMC proposal,
+// reading each restricted-set column of X once per leapfrog step (the reference reads it twice:
+// UpdatePredProb src/gibbs.cpp:179-188 and UpdateDNlogLike src/gibbs.cpp:239-249).
+//
+// Why one sweep suffices: MoveMomt of step t (gibbs.cpp:467-471) and UpdateMomtAndDeltas of step t+1
+// (gibbs.cpp:291-297) use the same DNlogpost, and both the gradient of column j and column j's
+// contribution to the next linear predictor need only column j plus the n x K residual. So while a
+// column sits in shared memory (and, within a thread, in registers) its owners compute g_j = X_j' r, apply
+// the two half kicks as two separate subtractions (bit-compatible with the reference), drift delta_j, and
+// accumulate X_j delta_j into their private lv partial. Algorithmic X traffic per iteration:
+// 8 n (L+1) u bytes (+ detach).
+//
+// Structure: 16 warps per block (4 per SM sub-partition, so a thread may use 128 registers), organised as
+// NG = 16/GW independent GROUPS of GW warps. A group owns whole columns (round robin over the block's
+// columns) and its own slice of the shared-memory ring:
+//   * one lane of the group (the duty rotates over its warps) streams the group's next columns in with
+//     cp.async.bulk (1-D TMA copies, completion counted on the stage's `full` mbarrier), SG-1 columns ahead of
+//     the one being consumed; the stream simply continues into the next leapfrog step, so the ring is full
+//     again when the block comes back from the grid-wide reduction. If the group's columns all fit in its
+//     ring they are loaded once and stay resident for the whole trajectory.
+//   * thread <-> NRP row pairs of the column, read once with unit-stride 128-bit shared-memory loads and kept
+//     in registers for both uses (the stage is handed back as soon as the loads have landed); the residual
+//     rows a thread needs live in registers for the sweep. Per column: dot products -> xor-shuffle tree ->
+//     (GW > 1) per-warp partials through shared memory and one named barrier of the group -> every thread
+//     forms the same gradient, prior gradient, MoveMomt / UpdateMomtAndDeltas (un-fused products) ->
+//     X_j delta_j accumulates into the thread's lv registers.
+//   Groups never wait for each other inside a sweep, so up to NG columns are in flight per SM; GW is the
+//   smallest group that keeps a thread's row pairs in registers.
+// After each sweep the group partials are summed in shared memory, the per-block lv partials are summed in
+// block order (deterministic), rows are soft-maxed and the new residual is published: two grid-wide barriers
+// per leapfrog step.
+//
+// Two flavours (template flag CL):
+//   grid mode    — one block per SM, cooperative launch; partials and residual travel through L2 and the two
+//                  barriers per step are release/acquire counters in global memory (~1.2 us each). Right when
+//                  the restricted set is large (HBM-bound).
+//   cluster mode — ONE thread-block cluster (16 CTAs, or 8); each block's lv partial stays in its own shared
+//                  memory and is read by the row owners through distributed shared memory, the new residual is
+//                  pushed into every block's shared memory, and the two barriers per step are hardware cluster
+//                  barriers. Right for small restricted sets (the product default, cut = 0.05), where a
+//                  leapfrog step is pure latency.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+
+#include "common.cuh"
+#include "launch.h"
+
+namespace htlr {
+
+namespace {
+
+constexpr int kCW = 16;                 // compute warps
+constexpr int kCT = kCW * 32;           // compute threads
+constexpr int kFT = kCT;                // every warp computes; TMA copies are issued by the groups themselves
+constexpr int kNlpMax = 2;              // row pairs per compute thread when publishing the lv partial (n <= 2048)
+constexpr int kPartSlots = 5;           // lv partials one lane sums in the row phase: grids of up to 160 blocks
+constexpr int kClMax = 16;              // largest cluster (non-portable size; 8 is the portable fallback)
+constexpr int kNsMax = 64;              // ring stages (one column each)
+constexpr int kBarGroup = 1;            // named barriers 1..4: the compute groups
+constexpr int kBarCompute = 5;          // all compute threads
+constexpr int kBarAll = 6;              // every thread of the block (grid barrier)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void named_bar(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Grid-wide barrier over all kFT threads of every block (blocks are co-resident: cooperative launch).
+// `counter` only ever grows during one launch; it is zeroed by k_begin before every trajectory.
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& gen, unsigned nblocks) {
+  named_bar(kBarAll, kFT);  // orders every thread's prior writes before thread 0's release below
+  if (threadIdx.x == 0) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+    const unsigned target = (gen + 1) * nblocks;
+    while (ld_acquire(counter) < target) { __nanosleep(32); }
+  }
+  named_bar(kBarAll, kFT);
+  ++gen;
+}
+__device__ __forceinline__ void cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ double ld_dsmem(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_dsmem(uint32_t addr, double v) {
+  asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ long long clk() {
+  long long t;
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory");
+  return t;
+}
+
+}  // namespace
+
+template <int KT>
+struct TileCols {
+  static constexpr int v = KT <= 2 ? 4 : 2;   // (column, class) values per tile: at most 8
+};
+
+template <int KT, int NRP, int GW, bool CL>
+__global__ void __launch_bounds__(kFT, 1) k_traj(Geom g, Bufs b, FusedGeom fg, int L) {
+  constexpr int NG = kCW / GW;           // compute groups
+  constexpr int GT = 32 * GW;            // threads per group
+  constexpr int CS = 3 * KT + 2;         // per-column state: d[K], m[K], prior gradient[K], sig, step
+  constexpr int TC = TileCols<KT>::v;    // columns per tile (= ring stage)
+  constexpr int V = TC * KT;             // (column, class) gradient values per tile
+  constexpr int VP = V <= 4 ? 4 : 8;     // padded to a power of two for the transposing reduction
+  Ctl* ctl = b.ctl;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int n = g.n, n_s = g.n_s, npairs = (n + 1) >> 1, n_e = 2 * npairs;
+  const int SG = fg.NS;                  // ring stages (tiles) per group
+  double* ring = reinterpret_cast<double*>(smem_raw);                       // [NG][SG][TC][n_e]
+  double* gpart = ring + (size_t)NG * SG * TC * n_e;                         // [2][kCW][VP] per-warp gradient partials
+  double* dnsm = gpart + 2 * kCW * VP;                                       // [2][NG][VP] new coefficients of a tile
+  double* lasm = dnsm + 2 * NG * VP;                                         // [KT][n_e] one group's lv partial in transit (NG > 1)
+  double* redsm = lasm + (NG > 1 ? (size_t)KT * n_e : 0);                    // [kCW]
+  double* dl = redsm + kCW;                                                  // [rpc*KT]
+  double* rowc = dl + ((fg.rpc * KT + 1) & ~1);                              // [rpc][2*KT+2] lv_fix, ymat, label
+  double* cst = rowc + (size_t)fg.rpc * (2 * KT + 2);                        // [ncmax][CS]
+  double* lp_own = cst + (((size_t)fg.ncmax * CS + 1) & ~(size_t)1);         // cluster mode: own lv partial [KT][n_e]
+  double* Rs = lp_own + (CL ? (size_t)KT * n_e : 0);                         // cluster mode: residual copy [KT][n_e]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Rs + (CL ? (size_t)KT * n_e : 0));
+  uint64_t* full = bars;                  // [NG*SG]  TMA -> group
+  int* cidx = reinterpret_cast<int*>(full + NG * SG);    // [ncmax] X column of each owned restricted-set position
+
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const unsigned G = gridDim.x;
+  const int cta = blockIdx.x;
+  const int u = ctl->u;
+  unsigned* gcounter = &ctl->ticket[4];
+  unsigned gen = 0;
+  if (CL) {
+    // restricted set too large for one cluster (state capacity, or past the size where grid mode is faster):
+    // leave the proposal to the grid-mode launch that follows
+    if (u > fg.cl_umax) return;
+  } else {
+    if (ctl->traj_done) return;   // the cluster-mode launch before this one already ran the trajectory
+  }
+  auto sync_all = [&]() {
+    if (CL) cluster_barrier(); else grid_barrier(gcounter, gen, G);
+  };
+
+  // ---- column ownership: contiguous ranges, only as many blocks as there are columns
+  const int gact = min((int)G, u);
+  int c0 = 0, c1 = 0;
+  if (cta < gact) {
+    c0 = (int)((int64_t)cta * u / gact);
+    c1 = (int)((int64_t)(cta + 1) * u / gact);
+  }
+  const int ncols = c1 - c0;
+  const uint32_t col_bytes = (uint32_t)npairs << 4;  // n rounded up to even, in bytes
+  const double Cd = (double)ctl->C;
+
+  if (tid == 0) {
+    for (int i = 0; i < NG * SG; ++i) mbar_init(&full[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (cta == 0) ctl->cols_swept += (unsigned long long)u * (unsigned long long)(L + 1);
+  }
+  // UpdateDNlogPrior / sigmasbt (gibbs.cpp:267-272, 281) depends only on the coefficients, so it is formed once
+  // per leapfrog step for all of the block's columns, off the per-tile critical path
+  auto prior_gradient = [&](int e) {
+    double* st = cst + (size_t)e * CS;
+    double sd = st[0];
+#pragma unroll
+    for (int k = 1; k < KT; ++k) sd += st[k];
+    const double sdc = sd / Cd, sig = st[3 * KT];
+#pragma unroll
+    for (int k = 0; k < KT; ++k) st[2 * KT + k] = (st[k] - sdc) / sig;
+  };
+  // this block's column indices and per-column state live in shared memory for the whole trajectory
+  for (int e = tid; e < ncols; e += kFT) {
+    const int r = c0 + e;
+    cidx[e] = b.iup[r];
+    double* st = cst + (size_t)e * CS;
+#pragma unroll
+    for (int k = 0; k < KT; ++k) { st[k] = b.dc[(int64_t)r * KT + k]; st[KT + k] = b.momt[(int64_t)r * KT + k]; }
+    st[3 * KT] = b.sigc[r];
+    st[3 * KT + 1] = b.stepc[r];
+    prior_gradient(e);
+  }
+  if (CL) {
+    for (int e = tid; e < KT * n_e; e += kFT) {
+      const int k = e / n_e, i = e - k * n_e;
+      Rs[e] = i < n ? b.R[(int64_t)k * n_s + i] : 0.0;
+    }
+  }
+  __syncthreads();
+
+  const int ct = tid;
+  const int grp = w / GW, wg = w % GW;
+  const int q = wg * 32 + lane;                 // thread index within the group
+  // the row pairs this thread covers in every column
+  int roff[NRP];
+  bool rval[NRP];
+#pragma unroll
+  for (int m = 0; m < NRP; ++m) {
+    const int rp = q + GT * m;
+    rval[m] = rp < npairs;
+    roff[m] = rval[m] ? 2 * rp : 0;
+  }
+  // ---- this group's tile stream: the block's columns are cut into tiles of TC; the group takes tiles
+  // grp, grp + NG, ...; the sequence repeats every leapfrog step. Tile i of the stream sits in stage i % SG of
+  // the group's ring; the copies for tile i + SG - 1 are issued when tile i is done. No `empty` barrier is
+  // needed: a stage is refilled only after the group's barriers of the tile that used it (program order for a
+  // one-warp group), and every thread reads its part of a tile into registers before those barriers. If the
+  // group's tiles all fit in its ring they are loaded once and stay resident for the trajectory.
+  const int ntiles = (ncols + TC - 1) / TC;
+  const int tpg = ntiles > grp ? (ntiles - grp + NG - 1) / NG : 0;     // tiles of this group per step
+  const bool resident = tpg <= SG;
+  const int64_t loads_total = resident ? tpg : (int64_t)tpg * (L + 1);
+  double* gring = ring + (size_t)grp * SG * TC * n_e;
+  uint64_t* gfull = full + grp * SG;
+  int64_t ld_left = loads_total;   // tiles of the stream still to request
+  int ld_tile = 0;                 // next one: position in the group's tile list (0 .. tpg-1)
+  int ld_stage = 0;                //           ring stage
+  int ld_warp = 0;                 //           issuing warp of the group (the duty rotates)
+  auto issue_one = [&]() {
+    if (wg == ld_warp) {
+      const int e0 = (grp + NG * ld_tile) * TC;
+      const int nc = min(TC, ncols - e0);
+      if (lane == 0) mbar_expect_tx(&gfull[ld_stage], col_bytes * (uint32_t)nc);
+      __syncwarp();
+      if (lane < nc)
+        bulk_g2s(gring + ((size_t)ld_stage * TC + lane) * n_e, b.X + (int64_t)cidx[e0 + lane] * g.ld, col_bytes,
+                 &gfull[ld_stage]);
+    }
+    --ld_left;
+    if (++ld_tile == tpg) ld_tile = 0;
+    if (++ld_stage == SG) ld_stage = 0;
+    if (++ld_warp == GW) ld_warp = 0;
+  };
+  {
+    const int pre = (int)(loads_total < SG - 1 ? loads_total : SG - 1);
+    for (int j = 0; j < pre; ++j) issue_one();
+  }
+
+  double Rg[NRP][2][KT];
+  // row phase: this thread's row of the block's row slice; its fixed part, label and one-hot row never
+  // change during a trajectory, so they are read once (into shared memory: registers are for the sweep)
+  const int row0 = cta * fg.rpc, nrows = max(0, min(n, row0 + fg.rpc) - row0);
+  if (ct < nrows) {
+    double* rc = rowc + (size_t)ct * (2 * KT + 2);
+    rc[2 * KT] = (double)b.ybase[row0 + ct];
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+      rc[k] = b.lv_fix[(int64_t)k * n_s + row0 + ct];
+      rc[KT + k] = b.ymat[(int64_t)k * n_s + row0 + ct];
+    }
+  }
+  const bool timer = (fg.timing != 0 && cta == 0 && tid == 0);   // only under htlr_cuda_profile_enable
+  long long tk0 = 0;   // phase cycle counters go straight to the control block (block 0, thread 0 only) as
+                       // fire-and-forget reductions: a read-modify-write would stall the warp on an L2 round trip
+  int tcount = 0;           // tiles this group has processed (parity selects the exchange buffers)
+  int pw = 0;               // warp of the group that applies the update to the current tile (the duty rotates)
+  int stage = 0;            // ring stage of the tile being consumed
+  uint32_t fph = 0;         // parity to wait for on its `full` barrier
+  // lane -> value index it holds after the transposing reduction, and whether it is the lane that stores it
+  const int vmine = VP == 8 ? (((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1))
+                            : (((lane >> 4) & 1) * 2 + ((lane >> 3) & 1));
+  const bool vwriter = (lane & (32 / VP - 1)) == 0;
+  for (int s = 0; s <= L; ++s) {
+    if (timer) tk0 = clk();
+    // residual rows of this thread into registers (published by the previous softmax phase)
+#pragma unroll
+    for (int m = 0; m < NRP; ++m) {
+#pragma unroll
+      for (int k = 0; k < KT; ++k) {
+        double r0v = 0, r1v = 0;
+        if (rval[m]) {
+          if (CL) {
+            const double2 rr = *reinterpret_cast<const double2*>(Rs + k * n_e + roff[m]);   // pad row holds 0
+            r0v = rr.x;
+            r1v = rr.y;
+          } else {
+            const double* Rk = b.R + (int64_t)k * n_s + roff[m];
+            r0v = __ldcg(Rk);
+            r1v = (roff[m] + 1 < n) ? __ldcg(Rk + 1) : 0.0;   // pad row of an odd n contributes nothing
+          }
+        }
+        Rg[m][0][k] = r0v;
+        Rg[m][1][k] = r1v;
+      }
+    }
+    double la[NRP][2][KT];
+#pragma unroll
+    for (int m = 0; m < NRP; ++m)
+#pragma unroll
+      for (int k = 0; k < KT; ++k) { la[m][0][k] = 0; la[m][1][k] = 0; }
+
+    if (resident) stage = 0;
+    for (int ti = 0; ti < tpg; ++ti, ++tcount) {
+      const int e0 = (grp + NG * ti) * TC;          // first block-local column of the tile
+      const int nc = min(TC, ncols - e0);           // columns in it (the block's last tile may be short)
+      const int buf = tcount & 1;
+      if (!resident || s == 0) mbar_wait(&gfull[stage], fph);
+      const double* tile = gring + (size_t)stage * TC * n_e;
+      // ---- the thread's rows of every column of the tile: the only shared-memory read of X
+      double2 x[TC][NRP];
+#pragma unroll
+      for (int c = 0; c < TC; ++c)
+#pragma unroll
+        for (int m = 0; m < NRP; ++m)
+          x[c][m] = (rval[m] && c < nc) ? *reinterpret_cast<const double2*>(tile + c * n_e + roff[m])
+                                        : make_double2(0.0, 0.0);
+      // ---- gradient partials of the tile (two independent chains per value)
+      double vals[VP];
+#pragma unroll
+      for (int c = 0; c < TC; ++c)
+#pragma unroll
+        for (int k = 0; k < KT; ++k) {
+          double a0 = 0, a1 = 0;
+#pragma unroll
+          for (int m = 0; m < NRP; ++m) {
+            a0 = fma(x[c][m].x, Rg[m][0][k], a0);
+            a1 = fma(x[c][m].y, Rg[m][1][k], a1);
+          }
+          vals[c * KT + k] = a0 + a1;
+        }
+#pragma unroll
+      for (int v = V; v < VP; ++v) vals[v] = 0;
+      // ---- transposing butterfly: halve the value set at each of the first log2(VP) levels, then plain xor
+      // levels; lane l ends up with the warp total of value vmine(l). Fixed order: deterministic.
+      {
+        int half = VP / 2;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+          if (half >= 1) {
+            const bool upper = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < VP / 2; ++i) {
+              if (i < half) {
+                const double send = upper ? vals[i] : vals[i + half];
+                const double keep = upper ? vals[i + half] : vals[i];
+                vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+              }
+            }
+            half >>= 1;
+          } else {
+            vals[0] += __shfl_xor_sync(0xffffffffu, vals[0], off);
+          }
+        }
+      }
+      double* gp = gpart + ((size_t)buf * kCW + grp * GW) * VP;
+      if (vwriter) gp[wg * VP + vmine] = vals[0];
+      if (GW > 1) named_bar(kBarGroup + grp, GT); else __syncwarp();
+      // ---- one warp of the group: DNlogpost, MoveMomt of step s, UpdateMomtAndDeltas of step s+1;
+      // lane <-> (column of the tile, class)
+      double* dnb = dnsm + ((size_t)buf * NG + grp) * VP;
+      if (wg == pw) {
+        if (lane < V) {
+          const int c = lane / KT, k = lane - c * KT;
+          double dnew = 0.0;
+          if (c < nc) {
+            double gsum = gp[lane];
+#pragma unroll
+            for (int ww = 1; ww < GW; ++ww) gsum += gp[ww * VP + lane];
+            double* st = cst + (size_t)(e0 + c) * CS;
+            const double dk = st[k], stp = st[3 * KT + 1], hs = stp / 2;
+            double mm = st[KT + k];
+            const double post = gsum + st[2 * KT + k];
+            const double kick = __dmul_rn(hs, post);
+            if (s >= 1) mm = __dsub_rn(mm, kick);
+            dnew = dk;
+            if (s < L) {
+              mm = __dsub_rn(mm, kick);
+              dnew = __dadd_rn(dk, __dmul_rn(stp, mm));
+            }
+            st[k] = dnew;
+            st[KT + k] = mm;
+          }
+          dnb[lane] = dnew;
+        }
+      }
+      if (GW > 1) named_bar(kBarGroup + grp, GT); else __syncwarp();
+      // ---- the tile's contribution to the next linear predictor, from the registers
+      if (s < L) {
+#pragma unroll
+        for (int c = 0; c < TC; ++c) {
+          if (c < nc) {
+#pragma unroll
+            for (int k = 0; k < KT; ++k) {
+              const double dnk = dnb[c * KT + k];
+#pragma unroll
+              for (int m = 0; m < NRP; ++m) {
+                la[m][0][k] = fma(x[c][m].x, dnk, la[m][0][k]);
+                la[m][1][k] = fma(x[c][m].y, dnk, la[m][1][k]);
+              }
+            }
+          }
+        }
+      }
+      // the stage this tile used is free again: request the tile SG-1 ahead into the stage released one tile ago
+      if (ld_left > 0) issue_one();
+      if (++stage == SG) { stage = 0; fph ^= 1; }
+      if (++pw == GW) pw = 0;
+    }
+    if (timer) { const long long t = clk(); atomicAdd(&ctl->ph_cycles[0], (unsigned long long)(t - tk0)); tk0 = t; }
+    if (s == L) break;
+
+    // ---- every group is done with the sweep: next step's prior-gradient terms, then this block's lv partial
+    named_bar(kBarCompute, kCT);
+    // groups 1.. hand their lv registers to group 0 one after the other through a one-group buffer (every group
+    // maps threads to rows the same way), group 0 adds them in group order
+    if (NG > 1) {
+#pragma unroll 1
+      for (int gg = 1; gg < NG; ++gg) {
+        if (ntiles <= gg) break;   // that group (and every later one) had no tile: nothing to add
+        if (grp == gg) {
+#pragma unroll
+          for (int m = 0; m < NRP; ++m) {
+            if (rval[m]) {
+#pragma unroll
+              for (int k = 0; k < KT; ++k)
+                *reinterpret_cast<double2*>(lasm + (size_t)k * n_e + roff[m]) = make_double2(la[m][0][k], la[m][1][k]);
+            }
+          }
+        }
+        named_bar(kBarCompute, kCT);
+        if (grp == 0) {
+#pragma unroll
+          for (int m = 0; m < NRP; ++m) {
+            if (rval[m]) {
+#pragma unroll
+              for (int k = 0; k < KT; ++k) {
+                const double2 t = *reinterpret_cast<const double2*>(lasm + (size_t)k * n_e + roff[m]);
+                la[m][0][k] += t.x;
+                la[m][1][k] += t.y;
+              }
+            }
+          }
+        }
+        named_bar(kBarCompute, kCT);
+      }
+    }
+    if (cta < gact && grp == 0) {
+#pragma unroll
+      for (int m = 0; m < NRP; ++m) {
+        if (rval[m]) {
+#pragma unroll
+          for (int k = 0; k < KT; ++k) {
+            double* o = CL ? lp_own + k * n_e + roff[m] : b.lvpart + ((int64_t)cta * KT + k) * n_s + roff[m];
+            *reinterpret_cast<double2*>(o) = make_double2(la[m][0][k], la[m][1][k]);
+          }
+        }
+      }
+    }
+    sync_all();
+    if (timer) { const long long t = clk(); atomicAdd(&ctl->ph_cycles[1], (unsigned long long)(t - tk0)); tk0 = t; }
+
+    // ---- sum the partials in block order, softmax, residual, log-likelihood (rows split over all blocks)
+    {
+      double l[KT];
+      if (CL) {
+        // thread <-> row: the partials sit in the owners' shared memory; every load is issued before the
+        // first add, the adds run in block order
+        if (ct < nrows) {
+          const uint32_t base = smem_u32(lp_own) + (uint32_t)(row0 + ct) * 8u;
+#pragma unroll
+          for (int k = 0; k < KT; ++k) {
+            double pv[kClMax];
+#pragma unroll
+            for (int qq = 0; qq < kClMax; ++qq)
+              pv[qq] = (qq < gact) ? ld_dsmem(map_to_cta(base + (uint32_t)(k * n_e) * 8u, (uint32_t)qq)) : 0.0;
+            double a = pv[0];
+#pragma unroll
+            for (int qq = 1; qq < kClMax; ++qq) a += pv[qq];
+            l[k] = rowc[(size_t)ct * (2 * KT + 2) + k] + a;
+          }
+        }
+      } else {
+        // one (row, class) item per warp pass; all of a lane's partials are requested before any is summed,
+        // so the pass costs one L2 round trip instead of one per 32 blocks
+        for (int item = w; item < nrows * KT; item += kCW) {
+          const int ii = item / KT, k = item - ii * KT;
+          const double* src = b.lvpart + (int64_t)k * n_s + row0 + ii;
+          double pv[kPartSlots];
+#pragma unroll
+          for (int qq = 0; qq < kPartSlots; ++qq) {
+            const int sl = lane + 32 * qq;
+            pv[qq] = (sl < gact) ? __ldcg(src + (int64_t)sl * KT * n_s) : 0.0;
+          }
+          double a = pv[0];
+#pragma unroll
+          for (int qq = 1; qq < kPartSlots; ++qq) a += pv[qq];
+          a = warp_sum(a);
+          if (lane == 0) dl[ii * KT + k] = a;
+        }
+        named_bar(kBarCompute, kCT);
+        if (ct < nrows) {
+#pragma unroll
+          for (int k = 0; k < KT; ++k) l[k] = rowc[(size_t)ct * (2 * KT + 2) + k] + dl[ct * KT + k];
+        }
+      }
+      // next step's prior-gradient terms, by the warps that hold no row of the softmax below (needed only
+      // after the second barrier)
+      {
+        int base = (nrows + 31) & ~31;
+        if (base >= kCT) base = 0;
+        if (ct >= base)
+          for (int e = ct - base; e < ncols; e += kCT - base) prior_gradient(e);
+      }
+      double ll = 0;
+      if (ct < nrows) {
+        const int i = row0 + ct;
+        const double* rc = rowc + (size_t)ct * (2 * KT + 2);
+        const int row_yb = (int)rc[2 * KT];
+        double m = 0.0;
+#pragma unroll
+        for (int k = 0; k < KT; ++k) m = fmax(m, l[k]);
+        double se = exp(0.0 - m);
+#pragma unroll
+        for (int k = 0; k < KT; ++k) se += exp(l[k] - m);
+        const double lse = log(se) + m;
+        if (row_yb == 0) ll = 0.0 - lse;
+#pragma unroll
+        for (int k = 0; k < KT; ++k) {
+          const double nl = l[k] - lse;
+          if (row_yb == k + 1) ll = nl;
+          const double res = exp(nl) - rc[KT + k];
+          b.lv[(int64_t)k * n_s + i] = l[k];
+          if (CL) {
+            // push the new residual into every block's copy
+            const uint32_t dst = smem_u32(Rs) + (uint32_t)(k * n_e + i) * 8u;
+#pragma unroll
+            for (int qq = 0; qq < kClMax; ++qq)
+              if (qq < (int)G) st_dsmem(map_to_cta(dst, (uint32_t)qq), res);
+          } else {
+            __stcg(&b.R[(int64_t)k * n_s + i], res);
+          }
+        }
+      }
+      ll = warp_sum(ll);
+      if (lane == 0) redsm[w] = ll;
+      named_bar(kBarCompute, kCT);
+      if (ct == 0) {
+        double t = 0;
+        for (int i = 0; i < kCW; ++i) t += redsm[i];
+        b.red[cta].c = t;
+      }
+    }
+    if (timer) { const long long t = clk(); atomicAdd(&ctl->ph_cycles[2], (unsigned long long)(t - tk0)); tk0 = t; }
+    sync_all();
+    if (timer) { const long long t = clk(); atomicAdd(&ctl->ph_cycles[3], (unsigned long long)(t - tk0)); }
+  }
+  // final coefficients and momenta back to the compact global arrays (every group has finished its tiles)
+  named_bar(kBarCompute, kCT);
+  for (int e = ct; e < ncols; e += kCT) {
+    const int r = c0 + e;
+    const double* st = cst + (size_t)e * CS;
+#pragma unroll
+    for (int k = 0; k < KT; ++k) { b.dc[(int64_t)r * KT + k] = st[k]; b.momt[(int64_t)r * KT + k] = st[KT + k]; }
+  }
+
+  // every block has passed the last grid-wide barrier, so all log-likelihood partials are visible
+  if (cta == 0 && tid == 0) {
+    double A = 0;
+    for (unsigned c = 0; c < G; ++c) A += __ldcg(&b.red[c].c);
+    ctl->loglike_new = A;
+    if (CL) ctl->traj_done = 1;
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------
+namespace {
+
+template <int KT, int NRP, int GW, bool CL>
+cudaError_t launch_one(const Geom& g, const Bufs& b, const FusedGeom& fg, int L, cudaStream_t st) {
+  static bool configured = false;
+  auto kern = k_traj<KT, NRP, GW, CL>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fg.smem_bytes_max);
+    if (e != cudaSuccess) return e;
+    if (CL && fg.cl > 8) {
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      if (e != cudaSuccess) return e;
+    }
+    configured = true;
+  }
+  Geom gg = g;
+  Bufs bb = b;
+  FusedGeom ff = fg;
+  int LL = L;
+  void* args[] = {&gg, &bb, &ff, &LL};
+  if (!CL) return cudaLaunchCooperativeKernel((void*)kern, dim3(fg.grid), dim3(kFT), args, fg.smem_bytes, st);
+  // one cluster: its CTAs are co-scheduled by construction, no cooperative launch needed
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(fg.grid);
+  cfg.blockDim = dim3(kFT);
+  cfg.dynamicSmemBytes = fg.smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = fg.cl;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelExC(&cfg, (void*)kern, args);
+}
+
+template <int KT, int NRP, bool CL>
+cudaError_t launch_gw(const Geom& g, const Bufs& b, const FusedGeom& fg, int L, cudaStream_t st) {
+  switch (fg.gw) {
+    case 1: return launch_one<KT, NRP, 1, CL>(g, b, fg, L, st);
+    case 4: return launch_one<KT, NRP, 4, CL>(g, b, fg, L, st);
+    case 8: return launch_one<KT, NRP, 8, CL>(g, b, fg, L, st);
+    case 16: return launch_one<KT, NRP, 16, CL>(g, b, fg, L, st);
+  }
+  return cudaErrorInvalidValue;
+}
+
+template <int KT, bool CL>
+cudaError_t launch_k(const Geom& g, const Bufs& b, const FusedGeom& fg, int L, cudaStream_t st) {
+  switch (fg.nrp) {
+    case 1: return launch_gw<KT, 1, CL>(g, b, fg, L, st);
+    case 2: return launch_gw<KT, 2, CL>(g, b, fg, L, st);
+  }
+  return cudaErrorInvalidValue;
+}
+
+template <bool CL>
+cudaError_t launch_mode(const Geom& g, const Bufs& b, const FusedGeom& fg, int L, cudaStream_t st) {
+  switch (g.K) {
+    case 1: return launch_k<1, CL>(g, b, fg, L, st);
+    case 2: return launch_k<2, CL>(g, b, fg, L, st);
+    case 3: return launch_k<3, CL>(g, b, fg, L, st);
+    case 4: return launch_k<4, CL>(g, b, fg, L, st);
+  }
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace
+
+// Picks the group width and ring depth for (n, K); returns false when the fused path does not apply (a column
+// must fit in shared memory with room for a pipeline, K <= 4). cl = 0: grid mode (one block per SM); cl > 0:
+// one cluster of cl blocks, which keeps per-column state for at most cl * ncmax restricted columns.
+bool fused_plan(const Geom& g, int smem_optin_bytes, int cl, FusedGeom* out) {
+  const int n = g.n, K = g.K;
+  if (K < 1 || K > 4) return false;
+  const int npairs = (n + 1) / 2, n_e = 2 * npairs;
+  if (npairs > kCT * kNlpMax) return false;
+  const int G = cl > 0 ? cl : g.sm_count;
+  if (cl > kClMax) return false;
+  const int rpc = (n + G - 1) / G;
+  if (rpc > kCT) return false;
+  if (G > 32 * kPartSlots) return false;   // row phase: one lane sums at most kPartSlots block partials
+  // smallest group whose threads keep their row pairs (x, residual, lv partial) in registers
+  const int nrp_max = 2;   // row pairs per thread: x (TC x NRP double2), residual and lv partial stay in registers
+  const int TC = K <= 2 ? 4 : 2;   // TileCols<K>
+  int gw = 0;
+  const char* force = std::getenv("HTLR_FUSED_GW");   // experiments only
+  for (int cand : {1, 4, 8, 16}) {
+    if (force && std::atoi(force) != cand) continue;
+    if ((npairs + 32 * cand - 1) / (32 * cand) <= nrp_max) { gw = cand; break; }
+  }
+  if (!gw) return false;
+  const int nrp = (npairs + 32 * gw - 1) / (32 * gw);
+  const int ng = kCW / gw;
+  const size_t col_bytes = (size_t)npairs * 16;
+  int ncmax;
+  if (cl > 0) ncmax = 160;   // columns per block the cluster keeps state for
+  else ncmax = (g.nvar + G - 1) / G + 1;   // worst case: every feature in the restricted set
+  const size_t other = (size_t)(2 * kCW * 8 + 2 * kCW * 8 + kCW + ((rpc * K + 1) & ~1) + rpc * (2 * K + 2) + 2) * sizeof(double) +
+                       (ng > 1 ? (size_t)K * n_e * sizeof(double) : 0) +
+                       (size_t)ncmax * ((3 * K + 2) * sizeof(double) + sizeof(int)) +
+                       (cl > 0 ? (size_t)2 * K * n_e * sizeof(double) : 0) + 2 * kNsMax * sizeof(uint64_t) + 256;
+  const size_t tile_bytes = (size_t)TC * col_bytes;
+  if ((size_t)smem_optin_bytes < other + 1024 + 2 * ng * tile_bytes) return false;
+  const size_t budget = (size_t)smem_optin_bytes - other - 1024;
+  const int SG = (int)std::min<size_t>(kNsMax / ng, budget / tile_bytes / ng);   // ring stages (tiles) per group
+  if (SG < 2) return false;
+  const int NS = SG;
+  out->T = TC; out->S = n_e; out->NS = NS; out->nrp = nrp; out->gw = gw; out->nlp = (npairs + kCT - 1) / kCT;
+  out->rpc = rpc;
+  out->grid = G;
+  out->cl = cl;
+  out->ncmax = ncmax;
+  out->smem_bytes = (size_t)NS * ng * tile_bytes + other;
+  out->smem_bytes_max = (size_t)smem_optin_bytes;
+  return true;
+}
+
+// Largest cluster (16, else 8) that can be resident with this shared-memory footprint, or 0.
+int fused_cluster_size(const Geom& g, int smem_optin_bytes) {
+  for (int cl = kClMax; cl >= 8; cl >>= 1) {
+    FusedGeom fg{};
+    if (!fused_plan(g, smem_optin_bytes, cl, &fg)) continue;
+    int nclusters = 0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cl);
+    cfg.blockDim = dim3(kFT);
+    cfg.dynamicSmemBytes = fg.smem_bytes;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cl;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    // every instantiation has the same launch bounds and dynamic shared memory, so one probe is enough
+    auto kern = k_traj<1, 1, 1, true>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin_bytes) != cudaSuccess) continue;
+    if (cl > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) continue;
+    if (cudaOccupancyMaxActiveClusters(&nclusters, (void*)kern, &cfg) == cudaSuccess && nclusters >= 1) return cl;
+    (void)cudaGetLastError();
+  }
+  (void)cudaGetLastError();
+  return 0;
+}
+
+cudaError_t launch_traj_fused(const Geom& g, const Bufs& b, const FusedGeom& fg, int L, cudaStream_t st) {
+  return fg.cl > 0 ? launch_mode<true>(g, b, fg, L, st) : launch_mode<false>(g, b, fg, L, st);
+}
+
+}  // namespace htlr

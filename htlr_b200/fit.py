@@ -56,21 +56,31 @@ class Sampler:
     def __init__(self, p, K, n, X, ymat, ybase, ptype, alpha, s, eta, iters_rmc, iters_h, thin, leap_L, leap_L_h,
                  leap_step, hmc_sgmcut, deltas, sigmasbt, keep_warmup_hist=False, silence=1, legacy=False, *,
                  device=0, rng_mode=RNG_DEVICE, seed=0, algo=0, use_graph=True, nccl_comm=None,
-                 ars_inject_width=0):
+                 ars_inject_width=0, device_ptrs=None):
+        """`device_ptrs=(X_ptr, ldx, ymat_ptr, ybase_ptr)`: the three n-sized inputs already live in device
+        memory (column-major FP64 with even leading dimension ldx; ybase int64) and `X`, `ymat`, `ybase` are
+        ignored — used for tall data generated on the GPU (htlr_cfg.x_on_device)."""
         L = _lib.lib()
         if isinstance(ptype, str):
             if ptype not in PTYPES:
                 raise HtlrCudaError(1, f"Unsupported prior type {ptype}")
             ptype = PTYPES[ptype]
-        X = _f64(X, "F")
-        if X.shape != (n, p + 1):
-            raise HtlrCudaError(1, f"X must be n x (p+1) = {n} x {p + 1}, got {X.shape}")
-        ymat = _f64(np.reshape(ymat, (n, K), order="F"), "F")
-        ybase = np.ascontiguousarray(ybase, dtype=np.int64)
+        if device_ptrs is None:
+            X = _f64(X, "F")
+            if X.shape != (n, p + 1):
+                raise HtlrCudaError(1, f"X must be n x (p+1) = {n} x {p + 1}, got {X.shape}")
+            ymat = _f64(np.reshape(ymat, (n, K), order="F"), "F")
+            ybase = np.ascontiguousarray(ybase, dtype=np.int64)
+            if ybase.shape != (n,):
+                raise HtlrCudaError(1, "ybase length mismatch")
+            xp, ldx, ymp, ybp = _ptr(X), n, _ptr(ymat), _ptr(ybase, c_lp)
+        else:
+            xp, ldx, ymp, ybp = (ctypes.cast(device_ptrs[0], c_dp), int(device_ptrs[1]),
+                                 ctypes.cast(device_ptrs[2], c_dp), ctypes.cast(device_ptrs[3], c_lp))
         deltas = _f64(np.reshape(deltas, (p + 1, K), order="F"), "F")
         sigmasbt = _f64(sigmasbt)
-        if ybase.shape != (n,) or sigmasbt.shape != (p + 1,):
-            raise HtlrCudaError(1, "ybase / sigmasbt length mismatch")
+        if sigmasbt.shape != (p + 1,):
+            raise HtlrCudaError(1, "sigmasbt length mismatch")
         self.p, self.K, self.n, self.nvar, self.C = p, K, n, p + 1, K + 1
         self.iters_rmc, self.iters_h, self.thin = iters_rmc, iters_h, thin
         self.leap_L, self.leap_L_h, self.leap_step = leap_L, leap_L_h, leap_step
@@ -83,13 +93,13 @@ class Sampler:
         cfg.leap_step, cfg.hmc_sgmcut = leap_step, hmc_sgmcut
         cfg.keep_warmup_hist, cfg.silence, cfg.legacy = int(keep_warmup_hist), int(silence), int(legacy)
         cfg.device, cfg.rng_mode, cfg.algo, cfg.seed = device, rng_mode, algo, seed
-        cfg.use_graph, cfg.x_on_device = int(use_graph), 0
+        cfg.use_graph, cfg.x_on_device = int(use_graph), 0 if device_ptrs is None else 1
         cfg.nccl_comm = nccl_comm
         cfg.ars_inject_width = ars_inject_width
         self.cfg = cfg
         self.h = ctypes.c_void_p()
-        rc = L.htlr_cuda_create(ctypes.byref(cfg), _ptr(X), n, _ptr(ymat), _ptr(ybase, c_lp), _ptr(deltas),
-                                _ptr(sigmasbt), ctypes.byref(self.h))
+        rc = L.htlr_cuda_create(ctypes.byref(cfg), xp, ldx, ymp, ybp, _ptr(deltas), _ptr(sigmasbt),
+                                ctypes.byref(self.h))
         if rc:
             raise HtlrCudaError(rc, L.htlr_cuda_last_error(None).decode())
         self.hist_len = L.htlr_cuda_hist_len(self.h)

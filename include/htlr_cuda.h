@@ -48,10 +48,15 @@ enum { HTLR_RNG_DEVICE = 0, HTLR_RNG_INJECT = 1 };
 
 /* Trajectory algorithm.
  * TWO_SWEEP: the reference's structure, one X sweep for lv and one for the gradient per leapfrog step.
- * FUSED    : persistent cooperative kernel, one X sweep per step (gradient, both half kicks, drift and the
- *            column's lv contribution from one staged copy of the column). Needs a column to fit in
- *            shared memory; AUTO picks it whenever it applies. */
-enum { HTLR_ALGO_AUTO = 0, HTLR_ALGO_TWO_SWEEP = 1, HTLR_ALGO_FUSED = 2 };
+ * FUSED    : persistent cooperative kernel over all SMs, one X sweep per step (gradient, both half kicks, drift
+ *            and the column's lv contribution from one staged copy of the column). Needs a column to fit in
+ *            shared memory; AUTO picks it whenever it applies.
+ * FUSED_CLUSTER: the same kernel run by ONE thread-block cluster that exchanges partial sums through
+ *            distributed shared memory and synchronises with hardware cluster barriers: lowest latency per
+ *            leapfrog step, for restricted sets of a few hundred columns (falls back to FUSED by itself when
+ *            the set is too large). AUTO launches both; the device picks one per iteration from the size of the
+ *            restricted set (cluster up to ~3 MB of X[:, iup]). */
+enum { HTLR_ALGO_AUTO = 0, HTLR_ALGO_TWO_SWEEP = 1, HTLR_ALGO_FUSED = 2, HTLR_ALGO_FUSED_CLUSTER = 3 };
 
 typedef struct htlr_handle htlr_handle;
 

@@ -21,7 +21,7 @@ def _pair(args, **gpu_kw):
 
 
 @pytest.mark.parametrize("n,p,C", [(62, 200, 2), (37, 90, 3), (500, 300, 4), (1000, 150, 3), (130, 60, 6),
-                                    (2500, 40, 3)])
+                                    (2500, 40, 3), (2300, 30, 5), (4100, 20, 7)])
 def test_eval_matches_oracle(n, p, C):
     args = problem(n, p, C, seed=n + p)
     gpu, ora = _pair(args)
@@ -50,7 +50,7 @@ def test_initial_state_matches_oracle():
     gpu.close()
 
 
-ALGOS = [pytest.param(1, id="two-sweep"), pytest.param(2, id="fused")]
+ALGOS = [pytest.param(1, id="two-sweep"), pytest.param(2, id="fused"), pytest.param(3, id="cluster")]
 
 
 @pytest.mark.parametrize("algo", ALGOS)
@@ -235,14 +235,16 @@ def test_fused_and_two_sweep_chains_agree():
     import htlr_b200
     args = problem(400, 600, 3, seed=31, iters_rmc=6, iters_h=6, leap_L=25)
     outs = []
-    for algo in (1, 2):
+    for algo in (1, 2, 3, 0):
         s = htlr_b200.Sampler(**args, seed=99, algo=algo)
-        s.run(12)
+        s.run(5)      # AUTO re-decides grid / cluster mode at every call from the restricted-set size it last saw
+        s.run(7)
         outs.append(s.fetch())
         s.close()
-    assert np.array_equal(outs[0]["mcuvar"], outs[1]["mcuvar"])
-    assert np.array_equal(outs[0]["mchmcrej"], outs[1]["mchmcrej"])
-    assert relerr(outs[0]["mcdeltas"], outs[1]["mcdeltas"]) < 1e-8
+    for o in outs[1:]:
+        assert np.array_equal(outs[0]["mcuvar"], o["mcuvar"])
+        assert np.array_equal(outs[0]["mchmcrej"], o["mchmcrej"])
+        assert relerr(outs[0]["mcdeltas"], o["mcdeltas"]) < 1e-8
 
 
 def test_fused_rejected_when_not_applicable():

@@ -10,9 +10,4 @@ args = bench.make_problem(a.workload)
 s = htlr_b200.Sampler(**dict(args, iters_h=a.warm, iters_rmc=a.iters), seed=7, algo=a.algo, use_graph=False)
 st = s.run(a.warm + a.iters)
 print("uvar", st["uvar"][-3:], "rej", st["rej"][-3:], "launches", s.launch_count)
-import ctypes
-out=(ctypes.c_ulonglong*16)()
-htlr_b200._lib.lib().htlr_cuda_debug_cycles(s.h, out)
-nst=sum((5 if i<a.warm else 50) for i in range(a.warm+a.iters))
-print("dbg ns/step blk0:", [round(out[q]/1.965/nst) for q in range(8)], "blk100:", [round(out[q]/1.965/nst) for q in range(8,16)])
 s.close()
