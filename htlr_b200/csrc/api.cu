@@ -84,14 +84,27 @@ struct htlr_handle {
   unsigned long long cols_base = 0;  // Ctl::cols_swept at the last profile reset
   unsigned long long ph_base[4] = {0, 0, 0, 0};
 
-  template <class T>
-  T* dalloc(size_t count, bool zero = true) {
+  // Device memory comes from a few large chunks (one cudaMalloc / cudaFree each): creating and destroying a
+  // handle then costs a handful of driver calls instead of ~50, which is what the end-to-end time of a short
+  // fit is made of.
+  struct Chunk { char* base; size_t size, used; };
+  std::vector<Chunk> chunks;
+  void arena_reserve(size_t bytes) {
     void* p = nullptr;
-    size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
     CU(cudaMalloc(&p, bytes));
     allocs.push_back(p);
+    chunks.push_back(Chunk{static_cast<char*>(p), bytes, 0});
+  }
+  template <class T>
+  T* dalloc(size_t count, bool zero = true) {
+    const size_t bytes = (std::max<size_t>(count, 1) * sizeof(T) + 255) & ~(size_t)255;
+    if (chunks.empty() || chunks.back().used + bytes > chunks.back().size)
+      arena_reserve(std::max<size_t>(bytes, (size_t)4 << 20));
+    Chunk& c = chunks.back();
+    char* p = c.base + c.used;
+    c.used += bytes;
     if (zero) CU(cudaMemsetAsync(p, 0, bytes, st));
-    return static_cast<T*>(p);
+    return reinterpret_cast<T*>(p);
   }
   int* ctl_int(size_t off) { return reinterpret_cast<int*>(reinterpret_cast<char*>(b.ctl) + off); }
   double* ctl_dbl(size_t off) { return reinterpret_cast<double*>(reinterpret_cast<char*>(b.ctl) + off); }
@@ -341,6 +354,18 @@ void do_create(const htlr_cfg* cfg, const double* X, int64_t ldx, const double* 
   g.e_grid = std::max(1, std::min((nvar + 255) / 256, 2 * g.sm_count));
 
   Bufs& b = h->b;
+  {
+    // everything create allocates, in one chunk (upper bound of the dalloc calls below + alignment slack)
+    const size_t Hh = (size_t)c.iters_rmc + 1 + (c.keep_warmup_hist ? c.iters_h : 0);
+    const size_t nkk = (size_t)g.n_s * K, nv = (size_t)nvar;
+    size_t dbl = (c.x_on_device ? 0 : (size_t)round_up(n, 16) * nv) + nkk + nv + nv * K + 2 * nv + 4 * nkk +
+                 2 * nv * K + 3 * nv + nv * K + 1 + (size_t)g.g_rt * nv * K +
+                 (size_t)std::max(g.lv_cs, g.sm_count) * K * g.n_s + Hh * (nv * (K + 2) + 4);
+    size_t bytes = dbl * sizeof(double) + ((size_t)n + 2 * nv) * sizeof(int) + nv +
+                   ((size_t)std::max(std::max(g.e_grid, (n + 255) / 256), g.sm_count) + c.iters_h + c.iters_rmc) * sizeof(Red4) +
+                   sizeof(Ctl) + 64 * 256;
+    h->arena_reserve(bytes);
+  }
   // ---- data
   if (c.x_on_device) {
     if (ldx % 2) FAIL(HTLR_E_ARG, "device-resident X needs an even leading dimension");
@@ -384,7 +409,6 @@ void do_create(const htlr_cfg* cfg, const double* X, int64_t ldx, const double* 
   b.R = h->dalloc<double>(nk);
   b.iup = h->dalloc<int>(nvar);
   b.ifix = h->dalloc<int>(nvar);
-  b.flags = h->dalloc<unsigned char>(nvar);
   b.dc = h->dalloc<double>((size_t)nvar * K);
   b.momt = h->dalloc<double>((size_t)nvar * K);
   b.stepc = h->dalloc<double>(nvar);

@@ -68,7 +68,6 @@ struct Bufs {
   const double *inj_norm, *inj_unif, *inj_gam, *inj_ars;
   // optional user momenta for htlr_cuda_trajectory (nvar x K col-major) or null
   const double* user_momt;
-  unsigned char* flags; // nvar scratch for the selection scan
 };
 
 void launch_colsumsq(const Geom& g, const double* X, double* ddn, cudaStream_t st);

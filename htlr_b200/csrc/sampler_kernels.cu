@@ -58,8 +58,9 @@ __global__ void k_colsumsq(Geom g, const double* __restrict__ X, double* __restr
 }
 
 // ------------------------------------------------------------------------------------------------
-// Ordered compaction of the restricted set by ONE block: thread t owns the contiguous chunk
-// [t*chunk, (t+1)*chunk) so ascending order falls out of an exclusive scan over per-thread counts.
+// Ordered compaction of the restricted set by ONE block of 32 warps: warp w owns the contiguous segment
+// [w*seg, (w+1)*seg) and walks it 32 features at a time (coalesced), so ascending order falls out of ballots:
+// pass 1 counts, an exclusive scan over the 32 warp totals gives each warp its output offset, pass 2 writes.
 __global__ void __launch_bounds__(1024) k_select(Geom g, Bufs b) {
   Ctl* ctl = b.ctl;
   __shared__ int s_w[32];
@@ -67,22 +68,19 @@ __global__ void __launch_bounds__(1024) k_select(Geom g, Bufs b) {
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int nvar = g.nvar;
   const double cut = ctl->init_all ? -1.0 : ctl->sgmsq_cut;
-  for (int j = tid; j < nvar; j += 1024) b.flags[j] = b.sigmasbt[j] > cut;
-  __syncthreads();
-  const int chunk = (nvar + 1023) / 1024;
-  const int j0 = min(nvar, tid * chunk), j1 = min(nvar, j0 + chunk);
-  int c = 0;
-  for (int j = j0; j < j1; ++j) c += b.flags[j];
-  int inc = c;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    int t = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += t;
+  const int seg = (((nvar + 31) / 32) + 31) & ~31;            // features per warp, a multiple of 32
+  const int j0 = min(nvar, w * seg), j1 = min(nvar, j0 + seg);
+  int cnt = 0;
+#pragma unroll 4
+  for (int j = j0 + lane; j - lane < j1; j += 32) {
+    const bool f = j < j1 && b.sigmasbt[j] > cut;
+    cnt += __popc(__ballot_sync(0xffffffffu, f));
   }
-  if (lane == 31) s_w[w] = inc;
+  if (lane == 0) s_w[w] = cnt;
   __syncthreads();
   if (w == 0) {
-    int v = s_w[lane], iv = v;
+    const int v = s_w[lane];
+    int iv = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       int t = __shfl_up_sync(0xffffffffu, iv, o);
@@ -92,10 +90,18 @@ __global__ void __launch_bounds__(1024) k_select(Geom g, Bufs b) {
     if (lane == 31) s_total = iv;
   }
   __syncthreads();
-  int pu = s_w[w] + inc - c;
-  int pf = j0 - pu;
-  for (int j = j0; j < j1; ++j) {
-    if (b.flags[j]) b.iup[pu++] = j; else b.ifix[pf++] = j;
+  int pu = s_w[w];       // next position in iup for this warp
+  int pf = j0 - pu;      // next position in ifix
+#pragma unroll 4
+  for (int j = j0 + lane; j - lane < j1; j += 32) {
+    const bool in = j < j1;
+    const bool f = in && b.sigmasbt[j] > cut;
+    const unsigned mu = __ballot_sync(0xffffffffu, f), mf = __ballot_sync(0xffffffffu, in && !f);
+    const unsigned below = (1u << lane) - 1u;
+    if (f) b.iup[pu + __popc(mu & below)] = j;
+    else if (in) b.ifix[pf + __popc(mf & below)] = j;
+    pu += __popc(mu);
+    pf += __popc(mf);
   }
   if (tid == 0) {
     const int u = s_total;
@@ -142,9 +148,12 @@ __global__ void __launch_bounds__(256) k_begin(Geom g, Bufs b) {
   pb = block_sum(pb, sm);
   if (threadIdx.x == 0) { b.red[blockIdx.x].a = pa; b.red[blockIdx.x].b = pb; }
   if (last_block(&ctl->ticket[0], gridDim.x)) {
+    // the block partials, summed by the whole block (fixed order: thread-strided, then block_sum's tree)
+    double A = 0, B = 0;
+    for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) { A += b.red[i].a; B += b.red[i].b; }
+    A = block_sum(A, sm);
+    B = block_sum(B, sm);
     if (threadIdx.x == 0) {
-      double A = 0, B = 0;
-      for (unsigned i = 0; i < gridDim.x; ++i) { A += b.red[i].a; B += b.red[i].b; }
       ctl->nenergy_old = ctl->loglike - A / 2 - B / 2;
       ctl->loglike_old = ctl->loglike;
       ctl->ticket[4] = 0;  // grid-barrier counter of the fused trajectory kernel
@@ -301,9 +310,10 @@ __global__ void __launch_bounds__(256) k_softmax(Geom g, Bufs b, int what, const
   ll = block_sum(ll, sm);
   if (threadIdx.x == 0) b.red[blockIdx.x].c = ll;
   if (last_block(&ctl->ticket[1], gridDim.x)) {
+    double A = 0;
+    for (unsigned q = threadIdx.x; q < gridDim.x; q += blockDim.x) A += b.red[q].c;
+    A = block_sum(A, sm);
     if (threadIdx.x == 0) {
-      double A = 0;
-      for (unsigned q = 0; q < gridDim.x; ++q) A += b.red[q].c;
       if (what == 1) ctl->loglike_new = A; else *loglike_out = A;
     }
   }
@@ -454,9 +464,12 @@ __global__ void __launch_bounds__(256) k_energy(Geom g, Bufs b, int g_has_loglik
   fault = block_sum(fault, sm);
   if (threadIdx.x == 0) { b.red[blockIdx.x].a = pa; b.red[blockIdx.x].b = pb; b.red[blockIdx.x].d = fault; }
   if (last_block(&ctl->ticket[2], gridDim.x)) {
+    double A = 0, B = 0, F = 0;
+    for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) { A += b.red[i].a; B += b.red[i].b; F += b.red[i].d; }
+    A = block_sum(A, sm);
+    B = block_sum(B, sm);
+    F = block_sum(F, sm);
     if (threadIdx.x == 0) {
-      double A = 0, B = 0, F = 0;
-      for (unsigned i = 0; i < gridDim.x; ++i) { A += b.red[i].a; B += b.red[i].b; F += b.red[i].d; }
       if (g_has_loglike) ctl->loglike_new = b.g[(int64_t)g.nvar * K];
       const double ne = ctl->loglike_new - A / 2 - B / 2;
       ctl->nenergy_new = ne;
