@@ -77,6 +77,8 @@ struct htlr_handle {
   double *t_lv = nullptr, *t_R = nullptr, *t_pred = nullptr, *t_coef = nullptr, *t_g = nullptr, *t_vd = nullptr,
          *t_momt = nullptr, *t_scalar = nullptr, *t_lvsave = nullptr;
   int *t_idx = nullptr, *t_cnt = nullptr;
+  double *s_mean = nullptr, *s_sdb = nullptr;   // posterior-summary scratch
+  int* s_flag = nullptr;
   Ctl* t_ctlsave = nullptr;
   // inject device buffers (addresses are baked into captured graphs)
   double *inj[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -811,6 +813,38 @@ int htlr_cuda_rng_dump(int32_t device, uint64_t seed, uint32_t purpose, uint64_t
     CU(cudaGetLastError());
     CU(cudaMemcpy(out, d, sizeof(double) * tot, cudaMemcpyDeviceToHost));
     cudaFree(d);
+  });
+}
+
+int htlr_cuda_summary(htlr_handle* h, int32_t first, int32_t last, int32_t thin, double cut, double* mean_deltas,
+                      double* sdb, int32_t* nzero) {
+  if (!h) return HTLR_E_ARG;
+  return guarded(h, [&] {
+    CU(cudaSetDevice(h->cfg.device));
+    const int H = htlr_cuda_hist_len(h);
+    if (first < 0) {
+      // htlr_sdb's default (R/mccoef.r:104-131): drop the warm-up slices and a further floor(0.2 * iter.rmc)
+      first = H - h->cfg.iters_rmc + (int)std::floor(0.2 * h->cfg.iters_rmc);
+      last = H - 1;
+    }
+    if (thin < 1 || first > last || last >= H) FAIL(HTLR_E_ARG, "bad slice range for the posterior summary");
+    const Geom& g = h->g;
+    const size_t nvar = g.nvar, K = g.K;
+    if (!h->s_mean) {
+      h->s_mean = h->dalloc<double>(nvar * K, false);
+      h->s_sdb = h->dalloc<double>(nvar, false);
+      h->s_flag = h->dalloc<int>(nvar, false);
+    }
+    double* d_mean = h->s_mean;
+    double* d_sdb = h->s_sdb;
+    int* d_flag = h->s_flag;
+    launch_trace_summary(g, h->b, first, last, thin, cut, d_mean, d_sdb, d_flag, h->st);
+    h->launches += 3;
+    CU(cudaStreamSynchronize(h->st));
+    CU(cudaGetLastError());
+    if (mean_deltas) CU(cudaMemcpy(mean_deltas, d_mean, nvar * K * sizeof(double), cudaMemcpyDeviceToHost));
+    if (sdb) CU(cudaMemcpy(sdb, d_sdb, (nvar - 1) * sizeof(double), cudaMemcpyDeviceToHost));
+    if (nzero) CU(cudaMemcpy(nzero, d_flag, (nvar - 1) * sizeof(int), cudaMemcpyDeviceToHost));
   });
 }
 

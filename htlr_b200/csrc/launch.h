@@ -95,6 +95,10 @@ void launch_vardeltas_all(const Geom& g, const Bufs& b, cudaStream_t st);
 void launch_scatter_proposal(const Geom& g, const Bufs& b, double* deltas_out, double* momt_out,
                              double* vd_out, cudaStream_t st);
 
+// posterior summaries from the device-resident trace (mean over slices first..last step thin, sdb, flags)
+void launch_trace_summary(const Geom& g, const Bufs& b, int first, int last, int thin, double cut, double* mean_out,
+                          double* sdb_out, int* flags_out, cudaStream_t st);
+
 // traj_kernel.cu
 bool fused_plan(const Geom& g, int smem_optin_bytes, int cl, FusedGeom* out);
 int fused_cluster_size(const Geom& g, int smem_optin_bytes);

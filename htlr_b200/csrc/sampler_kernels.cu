@@ -20,6 +20,7 @@
 // Layout: X column-major n x nvar with even leading dimension (each feature one contiguous column);
 // n-length arrays [k][i] with stride n_s; compact per-feature arrays indexed by position r in iup,
 // [r*K + k].
+#include <algorithm>
 #include <cstdio>
 
 #include "common.cuh"
@@ -580,7 +581,65 @@ __global__ void k_scatter_proposal(Geom g, Bufs b, double* deltas_out, double* m
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Posterior summaries straight from the device-resident trace (R/mccoef.r:119-156: summary(method = mean) over
+// the used slices, htlr_sdb = sqrt(comp_vardeltas(mean deltas)/C) without the intercept, nzero_idx =
+// which(sdb > cut * max(sdb))). Slices are summed in ascending order, one thread per coefficient.
+__global__ void k_trace_mean(Geom g, Bufs b, int first, int last, int thin, double* __restrict__ mean_out) {
+  const int64_t tot = (int64_t)g.nvar * g.K;
+  int cnt = 0;
+  for (int sidx = first; sidx <= last; sidx += thin) ++cnt;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < tot; e += (int64_t)gridDim.x * blockDim.x) {
+    double a = 0;
+    for (int sidx = first; sidx <= last; sidx += thin) a += b.mcdeltas[(int64_t)sidx * tot + e];
+    mean_out[e] = a / (double)cnt;
+  }
+}
+// sdb[j-1] for features j = 1..p and per-block maxima (red[].a)
+__global__ void __launch_bounds__(256) k_trace_sdb(Geom g, Bufs b, const double* __restrict__ mean, double* __restrict__ sdb) {
+  __shared__ double sm[32];
+  const int nvar = g.nvar, K = g.K;
+  const double Cd = (double)(K + 1);
+  double mx = 0;
+  for (int j = 1 + blockIdx.x * blockDim.x + threadIdx.x; j < nvar; j += gridDim.x * blockDim.x) {
+    double sd = mean[j], ss = __dmul_rn(sd, sd);
+    for (int k = 1; k < K; ++k) {
+      const double d = mean[(int64_t)k * nvar + j];
+      sd += d;
+      ss = __dadd_rn(ss, __dmul_rn(d, d));
+    }
+    const double v = sqrt((ss - __dmul_rn(sd, sd) / Cd) / Cd);   // comp_vardeltas (utils.cpp:51-56), comp_sdb (R/util.r:91-105)
+    sdb[j - 1] = v;
+    mx = fmax(mx, v);
+  }
+  // block maximum (values are >= 0 or NaN; fmax ignores NaN like R's max(..., na.rm) would not - documented)
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) sm[w] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t = fmax(t, sm[i]);
+    b.red[blockIdx.x].a = t;
+  }
+}
+__global__ void k_trace_nzero(Geom g, Bufs b, const double* __restrict__ sdb, double cut, int nblocks, int* __restrict__ flags) {
+  double mx = 0;
+  for (int i = 0; i < nblocks; ++i) mx = fmax(mx, b.red[i].a);
+  const double thr = cut * mx;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < g.nvar - 1; j += gridDim.x * blockDim.x) flags[j] = sdb[j] > thr;
+}
+
 // ================================================================================================
+void launch_trace_summary(const Geom& g, const Bufs& b, int first, int last, int thin, double cut, double* mean_out,
+                          double* sdb_out, int* flags_out, cudaStream_t st) {
+  const int64_t tot = (int64_t)g.nvar * g.K;
+  const int gm = (int)std::min<int64_t>((tot + 255) / 256, 8 * (int64_t)g.sm_count);
+  k_trace_mean<<<gm, 256, 0, st>>>(g, b, first, last, thin, mean_out);
+  k_trace_sdb<<<g.e_grid, 256, 0, st>>>(g, b, mean_out, sdb_out);
+  k_trace_nzero<<<g.e_grid, 256, 0, st>>>(g, b, sdb_out, cut, g.e_grid, flags_out);
+}
 void launch_colsumsq(const Geom& g, const double* X, double* ddn, cudaStream_t st) {
   k_colsumsq<<<g.sm_count * 4, 256, 0, st>>>(g, X, ddn);
 }

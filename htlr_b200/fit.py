@@ -161,6 +161,18 @@ class Sampler:
         out.update(o)
         return out
 
+    def summary(self, first=-1, last=-1, thin=1, cut=0.1):
+        """Posterior mean coefficients, htlr_sdb and nzero_idx (R/mccoef.r:38-62, 119-156) computed on the device
+        from the resident trace. Default slice range = htlr_sdb's (warm-up and a further 20 % dropped).
+        `nzero_idx` holds 1-based feature numbers like R's which()."""
+        nvar, K = self.nvar, self.K
+        mean = np.zeros((nvar, K), order="F")
+        sdb = np.zeros(self.p)
+        flags = np.zeros(self.p, dtype=np.int32)
+        self._check(_lib.lib().htlr_cuda_summary(self.h, first, last, thin, float(cut), _ptr(mean), _ptr(sdb),
+                                                 _ptr(flags, c_ip)))
+        return {"mean_deltas": mean, "sdb": sdb, "nzero_idx": np.nonzero(flags)[0] + 1}
+
     # -- deterministic pieces (parity hooks)
     def eval(self, iup, deltas):
         n, C, nvar, K = self.n, self.C, self.nvar, self.K

@@ -145,6 +145,15 @@ int htlr_cuda_fit(const htlr_cfg* cfg, const double* X, int64_t ldx, const doubl
                   double* mcsigmasbt, double* mcvardeltas, double* mclogw, double* mcloglike,
                   double* mcuvar, double* mchmcrej, double* ddnloglike, char* errbuf, size_t errbuf_len);
 
+/* Posterior summaries computed from the device-resident trace, so the (p+1) x K x H cube need not be fetched:
+ * mean of mcdeltas over slices first, first+thin, ... <= last (0-based; first < 0 selects htlr_sdb's default:
+ * warm-up slices and a further floor(0.2*iter.rmc) dropped), `summary(fit, method = mean)` R/mccoef.r:38-62;
+ * sdb[j-1] = sqrt(comp_vardeltas(mean deltas[j,])/C) for features j = 1..p, `htlr_sdb` R/mccoef.r:119-131 and
+ * `comp_sdb` R/util.r:91-105; nzero[j-1] = sdb[j-1] > cut * max(sdb), `nzero_idx` R/mccoef.r:151-155.
+ * mean_deltas (p+1) x K, sdb p, nzero p; any may be NULL. */
+int htlr_cuda_summary(htlr_handle* h, int32_t first, int32_t last, int32_t thin, double cut, double* mean_deltas,
+                      double* sdb, int32_t* nzero);
+
 /* ---- deterministic pieces, for the parity gate (level 1 of north_star) ---- */
 
 /* lv = X[:,iup] * deltas[iup,:] (nothing fixed), row-softmax, log-likelihood and gradient over iup:

@@ -43,3 +43,20 @@ def streams(args, seed=0, ars_width=0):
     if ars_width:
         out["ars_uniforms"] = g.random((T * (p + 1), ars_width))
     return out
+
+
+def posterior_summary(fit, burn=None, thin=1, cut=0.1):
+    """numpy restatement of the reference's posterior summaries for a fit dict (OutputR names):
+    get_sample_indice / htlr_sdb / nzero_idx (R/mccoef.r:104-156), summary(method = mean) (R/mccoef.r:38-62),
+    comp_sdb (R/util.r:91-105), comp_vardeltas (src/utils.cpp:51-56). Indices are R's 1-based ones."""
+    mcd = np.asarray(fit["mcdeltas"])
+    H = mcd.shape[2]
+    iter_rmc = fit["mc.param"]["iter.rmc"] if "mc.param" in fit else fit["iter.rmc"]
+    n_warm = H - iter_rmc
+    n_burn = int(np.floor(iter_rmc * 0.2)) if burn is None else burn
+    used = np.arange(n_warm + n_burn + 1, H + 1, thin)          # 1-based slice numbers, ignore.first = TRUE
+    mean = mcd[:, :, used - 1].mean(axis=2)
+    d = mean[1:]
+    C = d.shape[1] + 1
+    sdb = np.sqrt(synth.comp_vardeltas(d) / C)
+    return {"used": used, "mean_deltas": mean, "sdb": sdb, "nzero_idx": np.nonzero(sdb > cut * sdb.max())[0] + 1}
