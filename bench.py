@@ -38,8 +38,9 @@ WORKLOADS = {
                       desc="gendata_FAM n=1000 p=20000 C=3, t prior df=1, leap=50, cut=0.05 (htlr() defaults, restricted regime)"),
     "B": dict(gen="mlr", n=500, p=5000, C=4, cut=0.0, seed=1002,
               desc="gendata_MLR n=500 p=5000 C=4, t prior df=1, leap=50, cut=0"),
-    "D": dict(gen="mlr", n=200, p=50000, C=2, cut=0.0, seed=1004,
-              desc="gendata_MLR n=200 p=50000 C=2, t prior df=1, leap=50, cut=0 (one chain)"),
+    "D": dict(gen="mlr", n=200, p=50000, C=2, cut=0.05, seed=1004,
+              desc="independent chains of gendata_MLR n=200 p=50000 C=2, t prior df=1, leap=50, htlr() defaults (cut=0.05), "
+                   "several chains per GPU running concurrently, no communication"),
     "tiny": dict(gen="mlr", n=120, p=400, C=3, cut=0.0, seed=5, desc="tiny smoke workload"),
     # config E: ONE chain over all ranks, X row-sharded, NCCL all-reduce of the u x K gradient per leapfrog step
     "E": dict(gen="mlr_device", n=200000, p=10000, C=5, cut=0.0, seed=1005,
@@ -273,6 +274,81 @@ def measure_e2e(torch, wl, steps, device, chain_seed, dist):
     return (t1 - t0), h2d / steps, d2h / steps, warm_iters
 
 
+def measure_chains(torch, a, dist, rank, world, local):
+    """Config D: independent chains, `--chains-per-gpu` of them per GPU running CONCURRENTLY (each handle has its
+    own stream; CLUSTER_ONLY keeps every chain's trajectory on one 16-SM cluster so they overlap), no
+    communication. Also times the same chains one after the other for the concurrency gain."""
+    import htlr_b200
+    w = WORKLOADS["D"]
+    nch = a.chains_per_gpu
+    warm_iters = 150
+    total = warm_iters + a.warmup + 2 * a.steps
+    smps = []
+    for c in range(nch):
+        args = make_problem("D", chain_seed=rank * nch + c)
+        smps.append(htlr_b200.Sampler(**dict(args, iters_h=warm_iters, iters_rmc=total - warm_iters), device=local,
+                                      seed=5000 + rank * nch + c, algo=4))
+    for s in smps:
+        s.run(warm_iters + a.warmup)
+    streams = [torch.cuda.ExternalStream(s.stream) for s in smps]
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    # one after the other
+    seq_ms = 0.0
+    for s, st in zip(smps, streams):
+        e0, e1 = ev(), ev()
+        s.sync(); e0.record(st); s.run_async(a.steps); e1.record(st); s.sync()
+        seq_ms += e0.elapsed_time(e1)
+    # together
+    for s in smps:
+        s.sync()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = sum(s.launch_count for s in smps)
+    e0 = ev(); e0.record(streams[0])
+    ends = []
+    for s, st in zip(smps, streams):
+        s.run_async(a.steps)
+        e1 = ev(); e1.record(st); ends.append(e1)
+    for s in smps:
+        s.sync()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    ms = max(e0.elapsed_time(e) for e in ends)
+    launches = sum(s.launch_count for s in smps) - l0
+    uvar = []
+    for s in smps:
+        o = s.fetch()
+        uvar.append(float(np.mean(o["mcuvar"][-a.steps:])))
+        s.close()
+    t = torch.tensor([ms, seq_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        return
+    ms_max, seq_max = float(t[0]), float(t[1])
+    line = {"metric": "mcmc_iterations_per_sec", "value": world * nch * a.steps / (ms_max * 1e-3), "unit": "it/s",
+            "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_max / a.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": w["desc"], "regime": "restricted", "chains_per_gpu": nch, "chains_total": world * nch,
+                       "l2": "X[:, iup] of every chain is L2 / shared-memory resident (stated; latency-bound regime)",
+                       "parallelism": f"{nch} chains per GPU on separate streams, {world} GPU(s), no communication",
+                       "algorithm": "cluster-mode fused trajectory kernel (one 16-CTA cluster per chain)",
+                       "mean_nuvar": float(np.mean(uvar))},
+            "one_after_the_other": {"value": world * nch * a.steps / (seq_max * 1e-3), "unit": "it/s",
+                                    "concurrency_gain": seq_max / ms_max},
+            "e2e": None, "e2e_note": "measured on the default workload", "gpu_launches": launches,
+            "roofline": None, "roofline_note": "latency-bound regime (X[:, iup] of a chain is a few MB, L2 / shared-memory "
+                                               "resident); the HBM roofline is reported on the default workload"}
+    if not a.no_cpu_baseline:
+        rate, kind, m = cpu_reference_rate("D", 40, budget_s=25.0, warm_iters=150)
+        line["cpu_baseline"] = {"value": rate, "unit": "it/s", "cores": 1, "kind": kind,
+                                "sample": f"one chain, {m} sampling iterations after 150 warm-up iterations, 1 of "
+                                          f"{os.cpu_count()} host cores"}
+    print(json.dumps(line))
+
+
 def make_tall_on_device(torch, n_total, p, C, rank, world, seed):
     """gendata_MLR law (R/gendata.r:26-46) for this rank's row block, generated on the GPU (16 GB of X at
     full size never exists on the host). Coefficients come from the common seed, rows from seed + 1 + rank."""
@@ -383,6 +459,7 @@ def main():
     ap.add_argument("--no-secondary", action="store_true", help="skip the default-cut (restricted) block")
     ap.add_argument("--algo", type=int, default=0, help="0 auto (fused when applicable), 1 two-sweep, 2 fused")
     ap.add_argument("--n-total", type=int, default=0, help="workload E only: total rows (default 200000)")
+    ap.add_argument("--chains-per-gpu", type=int, default=4, help="workload D only")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
     # ONE JSON line on stdout: native libraries (NCCL banner, ...) print to fd 1, so park it on stderr and
@@ -413,6 +490,12 @@ def main():
 
     if a.workload == "E":
         measure_tall(torch, a, dist, rank, world, local)
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    if a.workload == "D":
+        measure_chains(torch, a, dist, rank, world, local)
         if dist is not None:
             dist.destroy_process_group()
         return

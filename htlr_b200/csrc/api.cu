@@ -198,8 +198,10 @@ int enqueue_step(htlr_handle* h, int L, bool until_energy_only = false) {
       CU(launch_traj_fused(g, b, h->fgc, L, st));
       ++nk;
     }
-    CU(launch_traj_fused(g, b, h->fg, L, st));
-    ++nk;
+    if (h->cfg.algo != HTLR_ALGO_CLUSTER_ONLY) {
+      CU(launch_traj_fused(g, b, h->fg, L, st));
+      ++nk;
+    }
   } else {
     gradient(0);
   }
@@ -256,7 +258,7 @@ cudaGraphExec_t get_graph(htlr_handle* h, int L) {
 int kernels_per_step(const htlr_handle* h, int L) {
   int per_grad = h->sharded ? 3 : 2;
   int n = 2 + 2 + per_grad + L * (2 + per_grad) + 1 + 1 + 1 + 1;
-  if (h->fused) n = 2 + 2 + 1 + 1 + 1 + 1 + 1 + (h->use_cluster ? 1 : 0);
+  if (h->fused) n = 2 + 2 + 1 + 1 + 1 + 1 + (h->cfg.algo == HTLR_ALGO_CLUSTER_ONLY ? 0 : 1) + (h->use_cluster ? 1 : 0);
   if (h->cfg.ptype == HTLR_PRIOR_T && h->cfg.eta > 1e-10) n += 1;
   return n;
 }
@@ -273,6 +275,9 @@ void check_device_error(htlr_handle* h) {
     case kErrInjectUniforms: FAIL(HTLR_E_SAMPLER, "injected uniforms exhausted");
     case kErrInjectGammas: FAIL(HTLR_E_SAMPLER, "injected gammas exhausted");
     case kErrInjectArs: FAIL(HTLR_E_SAMPLER, "injected ARS uniforms exhausted");
+    case kErrClusterCap:
+      FAIL(HTLR_E_SAMPLER, "restricted set (" + std::to_string(c.err_detail) +
+                               " features) exceeds the capacity of the cluster-only trajectory kernel");
     case kErrArs:
       switch (c.err_detail) {
         case 1: FAIL(HTLR_E_SAMPLER, "Error in adaptive rejection sampling:\nthe first tangent point doesn't have positive probability.\n");
@@ -424,7 +429,7 @@ void do_create(const htlr_cfg* cfg, const double* X, int64_t ldx, const double* 
     int coop = 0;
     CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c.device));
     const bool can = coop && !h->sharded && fused_plan(g, (int)prop.sharedMemPerBlockOptin, 0, &fgm);
-    if ((c.algo == HTLR_ALGO_FUSED || c.algo == HTLR_ALGO_FUSED_CLUSTER) && !can)
+    if ((c.algo == HTLR_ALGO_FUSED || c.algo == HTLR_ALGO_FUSED_CLUSTER || c.algo == HTLR_ALGO_CLUSTER_ONLY) && !can)
       FAIL(HTLR_E_ARG, "fused trajectory not applicable (needs K <= 4, a column tile in shared memory, one GPU)");
     h->fused = can && c.algo != HTLR_ALGO_TWO_SWEEP;
     h->fg = fgm;
@@ -439,10 +444,12 @@ void do_create(const htlr_cfg* cfg, const double* X, int64_t ldx, const double* 
         // crossover at about 3 MB of X[:, iup] (tools/mode_sweep.py).
         const int cap = h->fgc.cl * h->fgc.ncmax;
         const int by_bytes = (int)std::min<double>(3.0e6 / (8.0 * n), 2.0e9);
-        h->fgc.cl_umax = c.algo == HTLR_ALGO_FUSED_CLUSTER ? cap : std::min(cap, by_bytes);
+        const bool forced = c.algo == HTLR_ALGO_FUSED_CLUSTER || c.algo == HTLR_ALGO_CLUSTER_ONLY;
+        h->fgc.cl_umax = forced ? cap : std::min(cap, by_bytes);
+        h->fgc.cl_only = c.algo == HTLR_ALGO_CLUSTER_ONLY ? 1 : 0;
       }
     }
-    if (c.algo == HTLR_ALGO_FUSED_CLUSTER && !h->has_cluster)
+    if ((c.algo == HTLR_ALGO_FUSED_CLUSTER || c.algo == HTLR_ALGO_CLUSTER_ONLY) && !h->has_cluster)
       FAIL(HTLR_E_ARG, "cluster-mode trajectory kernel not available on this device");
     h->use_cluster = h->fused && h->has_cluster;
   }

@@ -15,6 +15,7 @@ enum DevErr : int {
   kErrInjectUniforms = 2,
   kErrInjectGammas = 3,
   kErrInjectArs = 4,
+  kErrClusterCap = 5,   // CLUSTER_ONLY: restricted set larger than the cluster keeps state for
   kErrArs = 16,  // + ArsStatus in err_detail
 };
 

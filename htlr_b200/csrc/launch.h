@@ -40,6 +40,7 @@ struct FusedGeom {
   int cl;      // 0: grid mode (cooperative launch); > 0: one thread-block cluster of this many blocks
   int ncmax;   // most restricted-set columns one block can own (state kept in shared memory)
   int cl_umax; // cluster mode runs the trajectory only while the restricted set has at most this many columns
+  int cl_only; // no grid-mode launch follows: exceeding cl_umax is an error
   int timing;  // 1: block 0 accumulates per-phase cycle counts into Ctl::ph_cycles (profiling runs only)
   size_t smem_bytes, smem_bytes_max;
 };

@@ -176,7 +176,10 @@ __global__ void __launch_bounds__(kFT, 1) k_traj(Geom g, Bufs b, FusedGeom fg, i
   if (CL) {
     // restricted set too large for one cluster (state capacity, or past the size where grid mode is faster):
     // leave the proposal to the grid-mode launch that follows
-    if (u > fg.cl_umax) return;
+    if (u > fg.cl_umax) {
+      if (fg.cl_only && cta == 0 && tid == 0) set_err(ctl, kErrClusterCap, u);
+      return;
+    }
   } else {
     if (ctl->traj_done) return;   // the cluster-mode launch before this one already ran the trajectory
   }
@@ -702,7 +705,8 @@ bool fused_plan(const Geom& g, int smem_optin_bytes, int cl, FusedGeom* out) {
   const int ng = kCW / gw;
   const size_t col_bytes = (size_t)npairs * 16;
   int ncmax;
-  if (cl > 0) ncmax = 160;   // columns per block the cluster keeps state for
+  if (cl > 0) ncmax = (int)(24 * 1024 / ((3 * K + 2) * sizeof(double) + sizeof(int))) & ~7;   // columns per block the
+                                                                       // cluster keeps state for (24 KB)
   else ncmax = (g.nvar + G - 1) / G + 1;   // worst case: every feature in the restricted set
   const size_t other = (size_t)(2 * kCW * 8 + 2 * kCW * 8 + kCW + ((rpc * K + 1) & ~1) + rpc * (2 * K + 2) + 2) * sizeof(double) +
                        (ng > 1 ? (size_t)K * n_e * sizeof(double) : 0) +

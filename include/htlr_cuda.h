@@ -55,8 +55,12 @@ enum { HTLR_RNG_DEVICE = 0, HTLR_RNG_INJECT = 1 };
  *            distributed shared memory and synchronises with hardware cluster barriers: lowest latency per
  *            leapfrog step, for restricted sets of a few hundred columns (falls back to FUSED by itself when
  *            the set is too large). AUTO launches both; the device picks one per iteration from the size of the
- *            restricted set (cluster up to ~3 MB of X[:, iup]). */
-enum { HTLR_ALGO_AUTO = 0, HTLR_ALGO_TWO_SWEEP = 1, HTLR_ALGO_FUSED = 2, HTLR_ALGO_FUSED_CLUSTER = 3 };
+ *            restricted set (cluster up to ~3 MB of X[:, iup]).
+ * CLUSTER_ONLY: FUSED_CLUSTER without the all-SM fallback launch, so that several chains (handles) can run
+ *            concurrently on one GPU, each on its own 16-SM cluster (config D: 4 chains / folds per GPU). A
+ *            restricted set beyond the cluster's capacity is HTLR_E_SAMPLER. */
+enum { HTLR_ALGO_AUTO = 0, HTLR_ALGO_TWO_SWEEP = 1, HTLR_ALGO_FUSED = 2, HTLR_ALGO_FUSED_CLUSTER = 3,
+       HTLR_ALGO_CLUSTER_ONLY = 4 };
 
 typedef struct htlr_handle htlr_handle;
 
