@@ -855,6 +855,47 @@ int htlr_cuda_summary(htlr_handle* h, int32_t first, int32_t last, int32_t thin,
   });
 }
 
+int htlr_cuda_predict(htlr_handle* h, const double* X_ts, int64_t ldx, int32_t n_ts, int32_t first, int32_t last,
+                      int32_t thin, double* probs) {
+  if (!h) return HTLR_E_ARG;
+  return guarded(h, [&] {
+    CU(cudaSetDevice(h->cfg.device));
+    const int H = htlr_cuda_hist_len(h);
+    if (first < 0) {
+      // htlr_predict's default (R/predict.R:43-49 with rep.legacy = TRUE): warm-up slices and a further
+      // floor(0.1 * iter.rmc) dropped, the first kept slice being the last dropped one (ignore.first = FALSE)
+      first = std::max(0, H - h->cfg.iters_rmc + (int)std::floor(0.1 * h->cfg.iters_rmc) - 1);
+      last = H - 1;
+    }
+    if (!X_ts || !probs || n_ts < 1 || ldx < n_ts) FAIL(HTLR_E_ARG, "bad test matrix");
+    if (thin < 1 || first > last || last >= H) FAIL(HTLR_E_ARG, "bad slice range for prediction");
+    if (h->sharded) FAIL(HTLR_E_STATE, "prediction is per GPU: call it on one rank (the trace is replicated)");
+    const Geom& g = h->g;
+    const size_t nvar = g.nvar, K = g.K;
+    const int S = (last - first) / thin + 1;
+    // scratch lives outside the handle's arena: test sets come and go
+    const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)S, ((size_t)256 << 20) / (sizeof(double) * n_ts * K)));
+    double *dA = nullptr, *dLV = nullptr, *dAcc = nullptr, *dP = nullptr;
+    auto cleanup = [&] { cudaFree(dA); cudaFree(dLV); cudaFree(dAcc); cudaFree(dP); };
+    try {
+      CU(cudaMalloc((void**)&dA, sizeof(double) * (size_t)n_ts * nvar));
+      CU(cudaMalloc((void**)&dLV, sizeof(double) * (size_t)n_ts * K * chunk));
+      CU(cudaMalloc((void**)&dAcc, sizeof(double) * (size_t)n_ts * K));
+      CU(cudaMalloc((void**)&dP, sizeof(double) * (size_t)n_ts * (K + 1)));
+      CU(cudaMemcpy2DAsync(dA, (size_t)n_ts * sizeof(double), X_ts, (size_t)ldx * sizeof(double),
+                           (size_t)n_ts * sizeof(double), nvar, cudaMemcpyHostToDevice, h->st));
+      h->launches += launch_predict(g, h->b, n_ts, dA, n_ts, first, thin, S, dLV, chunk, dAcc, dP, h->st);
+      CU(cudaStreamSynchronize(h->st));
+      CU(cudaGetLastError());
+      CU(cudaMemcpy(probs, dP, sizeof(double) * (size_t)n_ts * (K + 1), cudaMemcpyDeviceToHost));
+    } catch (...) {
+      cleanup();
+      throw;
+    }
+    cleanup();
+  });
+}
+
 void* htlr_cuda_stream(htlr_handle* h) { return h ? (void*)h->st : nullptr; }
 
 int htlr_cuda_profile_enable(htlr_handle* h, int32_t on) {

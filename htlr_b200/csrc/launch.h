@@ -100,6 +100,11 @@ void launch_scatter_proposal(const Geom& g, const Bufs& b, double* deltas_out, d
 void launch_trace_summary(const Geom& g, const Bufs& b, int first, int last, int thin, double cut, double* mean_out,
                           double* sdb_out, int* flags_out, cudaStream_t st);
 
+// predict_kernels.cu: averaged predictive probabilities of M cases from S trace slices (first, first+thin, ...);
+// LV is scratch for M x K x chunk doubles, accum for M x K; returns the number of kernels launched
+int launch_predict(const Geom& g, const Bufs& b, int M, const double* A, int64_t lda, int first, int thin, int S,
+                   double* LV, int chunk, double* accum, double* probs, cudaStream_t st);
+
 // traj_kernel.cu
 bool fused_plan(const Geom& g, int smem_optin_bytes, int cl, FusedGeom* out);
 int fused_cluster_size(const Geom& g, int smem_optin_bytes);

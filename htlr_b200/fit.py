@@ -173,6 +173,17 @@ class Sampler:
                                                  _ptr(flags, c_ip)))
         return {"mean_deltas": mean, "sdb": sdb, "nzero_idx": np.nonzero(flags)[0] + 1}
 
+    def predict(self, X_ts, first=-1, last=-1, thin=1):
+        """htlr_predict (R/predict.R:28-92) from the device-resident trace. `X_ts`: n_ts x (p+1), prepared like X
+        (selected features, standardised, intercept column). Returns n_ts x C probabilities."""
+        X_ts = _f64(np.atleast_2d(X_ts), "F")
+        if X_ts.shape[1] != self.nvar:
+            raise HtlrCudaError(1, f"X_ts must have p+1 = {self.nvar} columns")
+        n_ts = X_ts.shape[0]
+        probs = np.zeros((n_ts, self.C), order="F")
+        self._check(_lib.lib().htlr_cuda_predict(self.h, _ptr(X_ts), n_ts, n_ts, first, last, thin, _ptr(probs)))
+        return probs
+
     # -- deterministic pieces (parity hooks)
     def eval(self, iup, deltas):
         n, C, nvar, K = self.n, self.C, self.nvar, self.K

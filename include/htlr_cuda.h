@@ -158,6 +158,14 @@ int htlr_cuda_fit(const htlr_cfg* cfg, const double* X, int64_t ldx, const doubl
 int htlr_cuda_summary(htlr_handle* h, int32_t first, int32_t last, int32_t thin, double cut, double* mean_deltas,
                       double* sdb, int32_t* nzero);
 
+/* Predictive class probabilities of n_ts new cases, averaged over trace slices first, first+thin, ... <= last
+ * (0-based; first < 0 selects htlr_predict's default range), computed from the device-resident trace:
+ * the arithmetic of `htlr_predict` (R/predict.R:28-92). X_ts: n_ts x (p+1) column-major with leading dimension
+ * ldx, already feature-selected / standardised / with the intercept column, exactly like X at create.
+ * probs: n_ts x (K+1) column-major, column 0 = pmax(0, 1 - sum of the others). */
+int htlr_cuda_predict(htlr_handle* h, const double* X_ts, int64_t ldx, int32_t n_ts, int32_t first, int32_t last,
+                      int32_t thin, double* probs);
+
 /* ---- deterministic pieces, for the parity gate (level 1 of north_star) ---- */
 
 /* lv = X[:,iup] * deltas[iup,:] (nothing fixed), row-softmax, log-likelihood and gradient over iup:

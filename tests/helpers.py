@@ -60,3 +60,19 @@ def posterior_summary(fit, burn=None, thin=1, cut=0.1):
     C = d.shape[1] + 1
     sdb = np.sqrt(synth.comp_vardeltas(d) / C)
     return {"used": used, "mean_deltas": mean, "sdb": sdb, "nzero_idx": np.nonzero(sdb > cut * sdb.max())[0] + 1}
+
+
+def predict_reference(fit, X_ts, burn=None, thin=1):
+    """numpy restatement of htlr_predict (R/predict.R:28-92, rep.legacy = TRUE) for prepared X_ts (n_ts x (p+1))."""
+    mcd = np.asarray(fit["mcdeltas"])
+    H = mcd.shape[2]
+    iter_rmc = fit["mc.param"]["iter.rmc"] if "mc.param" in fit else fit["iter.rmc"]
+    n_burn = int(np.floor(iter_rmc * 0.1)) if burn is None else burn
+    used = np.arange(H - iter_rmc + n_burn + 0, H + 1, thin)     # 1-based, ignore.first = FALSE
+    used = used[used >= 1]
+    lv = np.einsum("ij,jks->iks", X_ts, mcd[:, :, used - 1])     # n_ts x K x S
+    full = np.concatenate([np.zeros_like(lv[:, :1]), lv], axis=1)
+    m = full.max(axis=1, keepdims=True)
+    lsl = np.log(np.exp(full - m).sum(axis=1, keepdims=True)) + m
+    probs = np.exp(lv - lsl).mean(axis=2)
+    return np.c_[np.maximum(0.0, 1.0 - probs.sum(axis=1)), probs]

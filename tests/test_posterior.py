@@ -105,3 +105,27 @@ def test_posterior_agrees_with_cpu_reference_within_mc_error():
         assert jac >= 0.6, (sa["nzero_idx"], sb["nzero_idx"])
         # acceptance behaviour is comparable
         assert abs(np.mean(fa["mchmcrej"][1:]) - np.mean(fb["mchmcrej"][1:])) < 0.15
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,p,C", [(90, 70, 4), (150, 333, 2), (60, 40, 3)])
+def test_device_prediction_matches_reference_formulas(n, p, C):
+    """htlr_cuda_predict against the numpy restatement of htlr_predict on the fetched trace (N2)."""
+    import htlr_b200
+    from tests.helpers import predict_reference, problem
+    args = problem(n, p, C, seed=n + C, iters_rmc=30, iters_h=10, keep_warmup_hist=(C == 3))
+    s = htlr_b200.Sampler(**args, seed=8)
+    s.run(40)
+    fit = s.fetch()
+    g = np.random.default_rng(1)
+    X_ts = np.c_[np.ones(77), g.standard_normal((77, p))]
+    a, b = s.predict(X_ts), predict_reference(fit, X_ts)
+    assert a.shape == (77, C)
+    assert relerr(a, b) < 1e-11
+    assert np.allclose(a.sum(1), 1.0, atol=1e-12)
+    a2 = s.predict(X_ts[:5], first=3, last=29, thin=4)
+    lv = np.einsum("ij,jks->iks", X_ts[:5], fit["mcdeltas"][:, :, 3:30:4])
+    full = np.concatenate([np.zeros_like(lv[:, :1]), lv], axis=1)
+    pr = np.exp(full - np.log(np.exp(full).sum(1, keepdims=True)))[:, 1:].mean(2)
+    assert relerr(a2[:, 1:], pr) < 1e-11
+    s.close()
