@@ -1,0 +1,125 @@
+"""Edge cases of the CUDA path against the oracle: smallest shapes, odd row counts, a restricted set that is only
+the intercept, many classes (generic kernels), one leapfrog step, thinning, long trajectories, the largest row
+count the fused kernel takes and the first one it does not."""
+import numpy as np
+import pytest
+
+from tests.helpers import problem, relerr, streams
+
+pytestmark = pytest.mark.gpu
+
+
+def _chain(args, algo, T=None, tol=1e-8, **kw):
+    import htlr_b200
+    from oracle import oracle as O
+    T = T or (args["iters_h"] + args["iters_rmc"])
+    st = streams(args, seed=5)
+    gpu = htlr_b200.Sampler(**args, rng_mode=htlr_b200.fit.RNG_INJECT, algo=algo, **kw)
+    ora = O.OracleFit(**args)
+    ora.initialize()
+    ora.set_inject(st["normals"], st["uniforms"], st["gammas"], None)
+    sg = gpu.run(T, **st)
+    ora.run(T)
+    so = ora.iter_stats()
+    assert np.array_equal(sg["uvar"], so["uvar"]) and np.array_equal(sg["rej"], so["rej"])
+    a, b = gpu.fetch(), ora.fetch()
+    for k in ("mcdeltas", "mcsigmasbt", "mcvardeltas", "mcloglike", "mcuvar", "mchmcrej"):
+        assert relerr(np.ravel(a[k]), np.ravel(b[k])) < tol, k
+    gpu.close()
+    return a
+
+
+ALGOS = [pytest.param(1, id="two-sweep"), pytest.param(2, id="fused"), pytest.param(3, id="cluster"),
+         pytest.param(0, id="auto")]
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("n,p,C", [(2, 1, 2), (3, 2, 3), (5, 1, 2), (31, 7, 5), (33, 3, 2), (63, 129, 4), (257, 5, 3)])
+def test_tiny_and_odd_shapes(n, p, C, algo):
+    args = problem(n, p, C, seed=n * 7 + p, iters_rmc=4, iters_h=3, leap_L=6, leap_L_h=2, hmc_sgmcut=0.0)
+    _chain(args, algo)
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_only_the_intercept_is_updated(algo):
+    """cut so large that no feature passes: iup = {intercept} (sigmab0 = 2000), u = 1 every iteration."""
+    args = problem(120, 40, 3, seed=3, iters_rmc=5, iters_h=3, hmc_sgmcut=30.0)
+    out = _chain(args, algo)
+    assert (out["mcuvar"][1:] == 1).all()
+
+
+@pytest.mark.parametrize("K1", [6, 9, 17])
+def test_many_classes_use_the_generic_kernels(K1):
+    """K = C - 1 > 4: no fused kernel, the two-sweep path with runtime K (up to 16)."""
+    import htlr_b200
+    args = problem(140, 30, K1, seed=K1, iters_rmc=3, iters_h=2, leap_L=4)
+    if K1 - 1 > 16:
+        with pytest.raises(htlr_b200.HtlrCudaError, match="K > 16"):
+            htlr_b200.Sampler(**args)
+        return
+    _chain(args, 0)
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_one_leapfrog_step_and_thinning(algo):
+    args = problem(90, 50, 3, seed=8, iters_rmc=4, iters_h=2, leap_L=1, leap_L_h=1, thin=3, keep_warmup_hist=True)
+    _chain(args, algo)
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_long_trajectory(algo):
+    args = problem(200, 30, 2, seed=5, iters_rmc=2, iters_h=1, leap_L=200, leap_L_h=3, leap_step=0.05, scale=0.2)
+    _chain(args, algo, tol=1e-7)
+
+
+@pytest.mark.parametrize("n", [2047, 2048, 2049, 3001])
+def test_row_count_around_the_fused_limit(n):
+    """n <= 2048 runs the fused kernel, above it AUTO falls back to the two-sweep path; both match the oracle."""
+    import htlr_b200
+    args = problem(n, 24, 3, seed=n, iters_rmc=2, iters_h=1, leap_L=5, hmc_sgmcut=0.0)
+    _chain(args, 0)
+    if n > 2048:
+        with pytest.raises(htlr_b200.HtlrCudaError, match="fused trajectory not applicable"):
+            htlr_b200.Sampler(**args, algo=2)
+
+
+def test_restricted_set_larger_than_the_cluster_falls_back_or_errors():
+    import htlr_b200
+    args = problem(64, 12000, 2, seed=1, iters_rmc=2, iters_h=1, leap_L=3, hmc_sgmcut=0.0)   # u = 12001 > cluster capacity
+    _chain(args, 3)                                  # FUSED_CLUSTER: grid-mode launch takes over
+    s = htlr_b200.Sampler(**args, algo=4, seed=1)    # CLUSTER_ONLY: reported as an error
+    with pytest.raises(htlr_b200.HtlrCudaError, match="exceeds the capacity"):
+        s.run(1)
+    s.close()
+
+
+def test_concurrent_chains_on_one_gpu_match_their_solo_runs():
+    """Config D's mode: several handles, separate streams, CLUSTER_ONLY; interleaving does not change a chain."""
+    import htlr_b200
+    args = problem(200, 300, 2, seed=2, iters_rmc=8, iters_h=4, leap_L=10)
+    solo = []
+    for c in range(3):
+        s = htlr_b200.Sampler(**args, seed=100 + c, algo=4)
+        s.run(12)
+        solo.append(s.fetch())
+        s.close()
+    ss = [htlr_b200.Sampler(**args, seed=100 + c, algo=4) for c in range(3)]
+    for it in range(12):
+        for s in ss:
+            s.run_async(1)
+    for c, s in enumerate(ss):
+        s.sync()
+        out = s.fetch()
+        for k in ("mcdeltas", "mcsigmasbt", "mcloglike", "mcuvar", "mchmcrej"):
+            assert np.array_equal(out[k], solo[c][k]), k
+        s.close()
+
+
+def test_run_past_the_end_is_refused():
+    import htlr_b200
+    args = problem(40, 10, 2, seed=1, iters_rmc=2, iters_h=1)
+    s = htlr_b200.Sampler(**args, seed=1)
+    s.run(3)
+    with pytest.raises(htlr_b200.HtlrCudaError, match="past the configured number"):
+        s.run(1)
+    s.close()
