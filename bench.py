@@ -32,8 +32,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    "C_full": dict(gen="fam", n=1000, p=20000, C=3, cut=0.0, seed=1003,
-                   desc="gendata_FAM n=1000 p=20000 C=3, t prior df=1, leap=50, cut=0 (all features updated: full X sweep per leapfrog step)"),
+    "C_full": dict(gen="fam", n=1000, p=20000, C=3, cut=0.0, seed=1003, leap_step=0.05,
+                   desc="gendata_FAM n=1000 p=20000 C=3, t prior df=1, leap=50, cut=0 (all features updated: full X sweep "
+                        "per leapfrog step), leap.stepsize=0.05 (the default 0.3 rejects every proposal when all 20001 "
+                        "features move; same cost per iteration)"),
     "C_default": dict(gen="fam", n=1000, p=20000, C=3, cut=0.05, seed=1003,
                       desc="gendata_FAM n=1000 p=20000 C=3, t prior df=1, leap=50, cut=0.05 (htlr() defaults, restricted regime)"),
     "B": dict(gen="mlr", n=500, p=5000, C=4, cut=0.0, seed=1002,
@@ -67,8 +69,11 @@ def make_problem(wl, chain_seed=0):
         d["y"][:w["C"]] = np.arange(w["C"])
     X, ymat, ybase, K = synth.make_inputs(d["X"], d["y"])
     deltas, sig = synth.init_state(w["p"], K, init="zero", seed=w["seed"] + 17 + chain_seed)
-    return dict(p=w["p"], K=K, n=w["n"], X=X, ymat=ymat, ybase=ybase, deltas=deltas, sigmasbt=sig,
-                hmc_sgmcut=w["cut"], **HTLR_DEFAULTS)
+    out = dict(p=w["p"], K=K, n=w["n"], X=X, ymat=ymat, ybase=ybase, deltas=deltas, sigmasbt=sig,
+               hmc_sgmcut=w["cut"], **HTLR_DEFAULTS)
+    if "leap_step" in w:
+        out["leap_step"] = w["leap_step"]
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -181,7 +186,7 @@ def run_reference_arm(a):
         rate *= E_CPU_ROWS / n_total
         scale_note = f"; timed on a {E_CPU_ROWS}-row sample of the same law and scaled linearly to n={n_total}"
     line = {"impl": "reference", "metric": "mcmc_iterations_per_sec", "value": rate, "unit": "it/s",
-            "n_gpus": a.gpus, "steps": m, "warmup": warm, "ms_per_step": 1e3 / rate, "higher_is_better": True,
+            "n_gpus": a.gpus, "steps": m, "warmup": a.warmup, "chain_warmup_iterations": warm, "ms_per_step": 1e3 / rate, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": w["desc"], "regime": "full" if w["cut"] <= 0 else "restricted"},
             "cpu_baseline": {"value": rate, "unit": "it/s", "cores": 1, "kind": kind,
