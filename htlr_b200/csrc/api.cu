@@ -355,7 +355,9 @@ void do_create(const htlr_cfg* cfg, const double* X, int64_t ldx, const double* 
   g.sm_count = prop.multiProcessorCount;
   g.lv_rt = (n + 511) / 512;
   g.lv_cs = (int)std::max<int64_t>(1, std::min<int64_t>((4 * g.sm_count + g.lv_rt - 1) / g.lv_rt, 1024));
-  g.g_tr = (int)std::min<int64_t>(g.n_s, K <= 4 ? 2048 : std::max(256, (8192 / K) / 64 * 64));
+  // residual tile of the gradient sweep: K * g_tr doubles <= 32 KB, so 6 blocks (48 warps) fit on an SM and keep
+  // ~100 KB of column loads in flight
+  g.g_tr = (int)std::min<int64_t>(g.n_s, std::max(256, (4096 / K) / 64 * 64));
   g.g_rt = (n + g.g_tr - 1) / g.g_tr;
   g.g_gx = std::max(1, (4 * g.sm_count + g.g_rt - 1) / g.g_rt);
   g.e_grid = std::max(1, std::min((nvar + 255) / 256, 2 * g.sm_count));

@@ -190,57 +190,79 @@ __device__ __forceinline__ ColSet resolve_cols(const Geom& g, const Bufs& b, int
 }
 
 // partial[cs][k][i] = sum over this block's share of the column set of X[i, j] * coef[j, k].
-// Thread = two consecutive rows (128-bit loads, 4 KB contiguous per block per column).
+// Thread = two consecutive rows (128-bit loads, 4 KB contiguous per block per column). The block's column
+// indices and coefficients are staged in shared memory in chunks (no dependent global loads in the loop, and
+// the streaming X loads bypass L1 allocation so they cannot evict anything useful); kU columns per pass keep
+// kU * 16 bytes per thread in flight.
+constexpr int kLvChunk = 512;   // columns staged per chunk
+__device__ __forceinline__ double2 ld_stream2(const double* p) {
+  double2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
 template <int KT>
 __global__ void __launch_bounds__(256) k_lv_sweep(Geom g, Bufs b, int mode, const int* idx_in,
                                                    const int* cnt_in, const double* coef_global) {
   constexpr int KM = KDim<KT>::kMax;
   const int K = KT > 0 ? KT : g.K;
+  extern __shared__ __align__(16) unsigned char lv_smem[];
+  double* s_coef = reinterpret_cast<double*>(lv_smem);                    // [kLvChunk][K]
+  int64_t* s_off = reinterpret_cast<int64_t*>(s_coef + (size_t)kLvChunk * K);  // [kLvChunk] column offsets (doubles)
   const ColSet cs = resolve_cols(g, b, mode, idx_in, cnt_in, coef_global);
   const int s = blockIdx.x;
   if (s == 0 && blockIdx.y == 0 && threadIdx.x == 0) b.ctl->cols_swept += (unsigned long long)cs.cnt;
   if (s >= cs.slots) return;
   const int c0 = (int)((int64_t)s * cs.cnt / cs.slots), c1 = (int)((int64_t)(s + 1) * cs.cnt / cs.slots);
   const int i = blockIdx.y * 512 + 2 * threadIdx.x;
-  if (i >= g.n) return;
+  const bool active = i < g.n;
   const bool tail = (i + 1 >= g.n);
   double a0[KM], a1[KM];
 #pragma unroll
   for (int k = 0; k < KM; ++k) { a0[k] = 0; a1[k] = 0; }
-  const double* Xi = b.X + i;
+  const double* Xi = b.X + (active ? i : 0);
   const int nvar = g.nvar;
-  int r = c0;
-  for (; r + 4 <= c1; r += 4) {
-    int j[4];
-    double2 x[4];
+  constexpr int kU = 8;
+  for (int ch0 = c0; ch0 < c1; ch0 += kLvChunk) {
+    const int cn = min(kLvChunk, c1 - ch0);
+    __syncthreads();   // the previous chunk is consumed
+    for (int e = threadIdx.x; e < cn; e += blockDim.x) {
+      const int j = __ldg(cs.idx + ch0 + e);
+      s_off[e] = (int64_t)j * g.ld;
+      for (int k = 0; k < K; ++k)
+        s_coef[e * K + k] = cs.cg ? __ldg(cs.cg + (int64_t)k * nvar + j) : __ldg(b.dc + (int64_t)(ch0 + e) * K + k);
+    }
+    __syncthreads();
+    if (!active) continue;
+    int r = 0;
+    for (; r + kU <= cn; r += kU) {
+      double2 x[kU];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) j[q] = __ldg(cs.idx + r + q);
+      for (int q = 0; q < kU; ++q) x[q] = ld_stream2(Xi + s_off[r + q]);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) x[q] = ldg2(Xi + (int64_t)j[q] * g.ld);
+      for (int q = 0; q < kU; ++q) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+        for (int k = 0; k < KM; ++k) {
+          if (k < K) {
+            const double c = s_coef[(r + q) * K + k];
+            a0[k] = fma(x[q].x, c, a0[k]);
+            a1[k] = fma(x[q].y, c, a1[k]);
+          }
+        }
+      }
+    }
+    for (; r < cn; ++r) {
+      const double2 x = ld_stream2(Xi + s_off[r]);
 #pragma unroll
       for (int k = 0; k < KM; ++k) {
         if (k < K) {
-          const double c = cs.cg ? __ldg(cs.cg + (int64_t)k * nvar + j[q]) : __ldg(b.dc + (int64_t)(r + q) * K + k);
-          a0[k] = fma(x[q].x, c, a0[k]);
-          a1[k] = fma(x[q].y, c, a1[k]);
+          const double c = s_coef[r * K + k];
+          a0[k] = fma(x.x, c, a0[k]);
+          a1[k] = fma(x.y, c, a1[k]);
         }
       }
     }
   }
-  for (; r < c1; ++r) {
-    const int j = __ldg(cs.idx + r);
-    const double2 x = ldg2(Xi + (int64_t)j * g.ld);
-#pragma unroll
-    for (int k = 0; k < KM; ++k) {
-      if (k < K) {
-        const double c = cs.cg ? __ldg(cs.cg + (int64_t)k * nvar + j) : __ldg(b.dc + (int64_t)r * K + k);
-        a0[k] = fma(x.x, c, a0[k]);
-        a1[k] = fma(x.y, c, a1[k]);
-      }
-    }
-  }
+  if (!active) return;
 #pragma unroll
   for (int k = 0; k < KM; ++k) {
     if (k < K) {
@@ -348,12 +370,13 @@ __global__ void __launch_bounds__(256) k_grad_sweep(Geom g, Bufs b, const int* i
 #pragma unroll
     for (int k = 0; k < KM; ++k) acc[k] = 0;
     int m = lane;
-    for (; m + 96 < pairs; m += 128) {
-      double2 x[4];
+    // 8 x 512 B per warp in flight per pass (HBM latency under load is ~2.5 us)
+    for (; m + 224 < pairs; m += 256) {
+      double2 x[8];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) x[q] = ldg2(xc + 2 * (m + 32 * q));
+      for (int q = 0; q < 8; ++q) x[q] = ld_stream2(xc + 2 * (m + 32 * q));
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < 8; ++q) {
         const int mm = m + 32 * q;
         if (2 * mm + 1 >= rows) x[q].y = 0;
 #pragma unroll
@@ -367,7 +390,7 @@ __global__ void __launch_bounds__(256) k_grad_sweep(Geom g, Bufs b, const int* i
       }
     }
     for (; m < pairs; m += 32) {
-      double2 x = ldg2(xc + 2 * m);
+      double2 x = ld_stream2(xc + 2 * m);
       if (2 * m + 1 >= rows) x.y = 0;
 #pragma unroll
       for (int k = 0; k < KM; ++k) {
@@ -649,7 +672,15 @@ void launch_begin(const Geom& g, const Bufs& b, cudaStream_t st) { k_begin<<<g.e
 void launch_lv_sweep(const Geom& g, const Bufs& b, int mode, const int* idx, const int* cnt,
                      const double* coef_global, cudaStream_t st) {
   dim3 grid(g.lv_cs, g.lv_rt);
-  DISPATCH_K(g.K, k_lv_sweep<KT><<<grid, 256, 0, st>>>(g, b, mode, idx, cnt, coef_global));
+  const size_t smem = (size_t)kLvChunk * (g.K * sizeof(double) + sizeof(int64_t));   // <= 36 KB at K = 16... see below
+  DISPATCH_K(g.K, {
+    static bool configured = false;
+    if (!configured) {
+      cudaFuncSetAttribute(k_lv_sweep<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
+      configured = true;
+    }
+    k_lv_sweep<KT><<<grid, 256, smem, st>>>(g, b, mode, idx, cnt, coef_global);
+  });
 }
 void launch_softmax(const Geom& g, const Bufs& b, int what, const int* cnt, double* lv_out, double* R_out,
                     double* pred_out, double* loglike_out, cudaStream_t st) {
