@@ -36,6 +36,12 @@ constexpr int kArsCap = 32;
 constexpr int kArsMaxTries = 4096;
 constexpr double kArsStepout = 10.0, kArsTolD = 1e-5, kArsTolDD = 1e-5;
 
+// exp / log are called from ~40 places in the engine and the targets; inlining them all makes a 220 KB kernel
+// whose warps (each at a different point of its own accept/reject loop) thrash the instruction cache
+// (ncu: 43 % of stalls were `no_instruction`). One out-of-line copy of each keeps the loop cache-resident.
+__device__ __noinline__ double ars_exp(double x) { return exp(x); }
+__device__ __noinline__ double ars_log(double x) { return log(x); }
+
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 __device__ __forceinline__ int shfl_i(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
@@ -43,9 +49,9 @@ __device__ __forceinline__ int shfl_i(int v, int src) { return __shfl_sync(0xfff
 __device__ __forceinline__ double ars_logint(double f, double df, double t, double lo, double hi) {
   double dx = hi - lo;
   double adf = fabs(df);
-  if (adf <= kArsTolD) return f + log(dx);
+  if (adf <= kArsTolD) return f + ars_log(dx);
   double edge = df > kArsTolD ? hi : lo;
-  return f + df * (edge - t) - log(adf) + log(1 - exp(-adf * dx));
+  return f + df * (edge - t) - ars_log(adf) + ars_log(1 - ars_exp(-adf * dx));
 }
 // ars.cpp:453-462
 __device__ __forceinline__ double ars_cross(double t1, double t2, double f1, double f2, double d1, double d2) {
@@ -71,6 +77,22 @@ struct ArsArrayUniforms {
     if (c >= n) return false;
     v = u[c++];
     return true;
+  }
+};
+
+// One source type for both random-number modes (a runtime switch instead of two instantiations of the engine).
+struct ArsUniforms {
+  bool inject;          // host-supplied block (u, n) or the keyed Philox stream
+  const double* u;
+  int n, c;
+  ArsKeyedUniforms keyed;
+  __device__ __forceinline__ bool next(double& v) {
+    if (inject) {
+      if (c >= n) return false;
+      v = u[c++];
+      return true;
+    }
+    return keyed.next(v);
   }
 };
 
@@ -173,7 +195,7 @@ struct ArsWarp {
       double mx = lane < nh ? H.lw : -INFINITY;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      double e = lane < nh ? exp(H.lw - mx) : 0.0;
+      double e = lane < nh ? ars_exp(H.lw - mx) : 0.0;
       double acc = 0.0, cw = 0.0;
       for (int i = 0; i < nh; ++i) {
         acc += shfl_d(e, i);
@@ -199,13 +221,13 @@ struct ArsWarp {
       if (!un.next(y)) return kArsNoUniforms;
       ++n_unif;
       if (type == 0) x = lo + y * dx;
-      else if (type == 1) x = hi + log((1 - y) * exp(-dh * dx) + y) / dh;
-      else x = lo + log(1 - y + y * exp(dh * dx)) / dh;
+      else if (type == 1) x = hi + ars_log((1 - y) * ars_exp(-dh * dx) + y) / dh;
+      else x = lo + ars_log(1 - y + y * ars_exp(dh * dx)) / dh;
       const double upper = (x - th) * dh + fh;
       double ua;
       if (!un.next(ua)) return kArsNoUniforms;
       ++n_unif;
-      const double logacc = upper + log(ua);
+      const double logacc = upper + ars_log(ua);
       const double slope = x >= th ? shfl_d(H.sr, h) : shfl_d(H.sl, h);
       const double lower = (x - th) * slope + fh;
       if (logacc <= lower) { x_out = x; return kArsOk; }
@@ -223,21 +245,21 @@ struct SgmTarget {
   int kind;  // 1 ghs, 2 neg
   double v, K, alpha, log_aw;
   __device__ __forceinline__ void operator()(double x, double& logf, double& dlogf) const {
-    const double vexi = v / 2.0 / exp(x);
-    const double e = exp(x - log_aw);
+    const double vexi = v / 2.0 / ars_exp(x);
+    const double e = ars_exp(x - log_aw);
     if (kind == 2) {
       logf = -(K / 2.0 - 1.0) * x;
       dlogf = -(K / 2.0 - 1.0);
       logf -= vexi;
       dlogf += vexi;
-      logf -= (alpha / 2.0 + 1.0) * log(1.0 + 2.0 * e);
+      logf -= (alpha / 2.0 + 1.0) * ars_log(1.0 + 2.0 * e);
       dlogf -= (alpha + 2.0) * e / (1.0 + 2.0 * e);
     } else {
       logf = -(K - 1.0) / 2.0 * x;
       dlogf = -(K - 1.0) / 2.0;
       logf -= vexi;
       dlogf += vexi;
-      logf -= (alpha + 1.0) / 2.0 * log(1.0 + e);
+      logf -= (alpha + 1.0) / 2.0 * ars_log(1.0 + e);
       dlogf -= (alpha + 1.0) / 2.0 * e / (1.0 + e);
     }
   }

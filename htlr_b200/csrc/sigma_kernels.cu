@@ -47,14 +47,15 @@ __global__ void __launch_bounds__(256) k_sigma_ars(Geom g, Bufs b) {
     const double x0 = log(tg.v / tg.K);
     double x = 0;
     int status;
-    if (ctl->rng_mode == 1) {
-      const long long blk = ctl->step_in_call * (long long)(p + 1) + q;
-      ArsArrayUniforms un{b.inj_ars + blk * ctl->ars_width, blk < ctl->n_ars_blocks ? ctl->ars_width : 0, 0};
-      ArsWarp<SgmTarget, ArsArrayUniforms> ars(tg, un);
-      status = ars.sample(x0, x);
-    } else {
-      ArsKeyedUniforms un{ctl->seed, ctl->step, kRngArs, (uint32_t)j, 0u};
-      ArsWarp<SgmTarget, ArsKeyedUniforms> ars(tg, un);
+    {
+      ArsUniforms un{false, nullptr, 0, 0, ArsKeyedUniforms{ctl->seed, ctl->step, kRngArs, (uint32_t)j, 0u}};
+      if (ctl->rng_mode == 1) {
+        un.inject = true;
+        const long long blk = ctl->step_in_call * (long long)(p + 1) + q;
+        un.u = b.inj_ars + blk * ctl->ars_width;
+        un.n = blk < ctl->n_ars_blocks ? ctl->ars_width : 0;
+      }
+      ArsWarp<SgmTarget, ArsUniforms> ars(tg, un);
       status = ars.sample(x0, x);
     }
     if (status != kArsOk) {
