@@ -450,6 +450,12 @@ def measure_tall(torch, a, dist, rank, world, local):
                          "peak_source": peak_src, "launches_timed": pr["sweep_launches"],
                          "algorithmic_bytes_per_launch": pr["sweep_bytes"] / max(pr["sweep_launches"], 1),
                          "sweep_share_of_step": pr["sweep_ms"] / max(pr["total_ms"], 1e-9)}}
+    if not a.no_cpu_baseline:
+        rate, kind, m = cpu_reference_rate("E", 3, budget_s=25.0, warm_iters=0)
+        line["cpu_baseline"] = {"value": rate * E_CPU_ROWS / n_total, "unit": "it/s", "cores": 1, "kind": kind,
+                                "sample": f"{m} sampling iterations on a {E_CPU_ROWS}-row sample of the same law, scaled "
+                                          f"linearly to n={n_total} (the reference's cost is linear in n); 1 of "
+                                          f"{os.cpu_count()} host cores"}
     print(json.dumps(line))
 
 
