@@ -38,8 +38,10 @@ WORKLOADS = {
                         "features move; same cost per iteration)"),
     "C_default": dict(gen="fam", n=1000, p=20000, C=3, cut=0.05, seed=1003,
                       desc="gendata_FAM n=1000 p=20000 C=3, t prior df=1, leap=50, cut=0.05 (htlr() defaults, restricted regime)"),
-    "B": dict(gen="mlr", n=500, p=5000, C=4, cut=0.0, seed=1002,
-              desc="gendata_MLR n=500 p=5000 C=4, t prior df=1, leap=50, cut=0"),
+    "B": dict(gen="mlr", n=500, p=5000, C=4, cut=0.0, seed=1002, leap_step=0.05,
+              desc="gendata_MLR n=500 p=5000 C=4, t prior df=1, leap=50, cut=0 (all features updated), leap.stepsize=0.05"),
+    "B_default": dict(gen="mlr", n=500, p=5000, C=4, cut=0.05, seed=1002,
+                      desc="gendata_MLR n=500 p=5000 C=4, t prior df=1, leap=50, htlr() defaults (cut=0.05)"),
     "D": dict(gen="mlr", n=200, p=50000, C=2, cut=0.05, seed=1004,
               desc="independent chains of gendata_MLR n=200 p=50000 C=2, t prior df=1, leap=50, htlr() defaults (cut=0.05), "
                    "several chains per GPU running concurrently, no communication"),
@@ -536,6 +538,27 @@ def main():
                      "fused_phase_ms_per_launch_block0": {k: r2["prof"][k] / max(r2["prof_steps"], 1) for k in
                                                           ("fused_sweep_ms", "fused_barrier_ms", "fused_rowphase_ms")},
                      "note": "restricted regime: X[:,iup] is L2-resident, bound by launch/sync latency not HBM"}
+    others = None
+    if not a.no_secondary and a.workload == "C_full" and rank == 0:
+        # config B (BASELINE configs[1]) in both regimes, and one whole default run of config C
+        # (htlr() defaults: iter = 2000, warmup = 1000) through the public entry point with host buffers
+        others = {}
+        for name, wl_name in (("B_default_cut", "B_default"), ("B_full", "B")):
+            rb = measure_workload(torch, wl_name, 200, a.warmup, local, rank, None, want_profile=False)
+            others[name] = {"workload": WORKLOADS[wl_name]["desc"], "value": 200 / (rb["ms"] * 1e-3), "unit": "it/s",
+                            "ms_per_step": rb["ms"] / 200, "mean_nuvar": rb["uvar"], "hmc_reject": rb["rej"],
+                            "gpu_launches": rb["launches"]}
+        import htlr_b200
+        args = make_problem("C_default")
+        t0 = time.perf_counter()
+        out = htlr_b200.htlr_fit_helper(**dict(args, iters_h=1000, iters_rmc=1000), device=local, seed=4242)
+        dt = time.perf_counter() - t0
+        others["C_whole_default_run"] = {"what": "htlr() defaults on config C through htlr_fit_helper with host buffers: "
+                                                 "1000 warm-up iterations (leap.warm = 5) + 1000 sampling iterations "
+                                                 "(leap = 50), H2D of X, D2H of the 1001-slice trace",
+                                         "seconds": dt, "value": 2000 / dt, "unit": "it/s",
+                                         "mean_nuvar_sampling": float(np.mean(out["mcuvar"][1:])),
+                                         "hmc_reject_sampling": float(np.mean(out["mchmcrej"][1:]))}
     if dist is not None:
         dist.barrier()
 
@@ -578,6 +601,8 @@ def main():
         }
         if secondary:
             line["default_cut"] = secondary
+        if others:
+            line["other_configs"] = others
         if not a.no_cpu_baseline:
             rate, kind, m = cpu_reference_rate(a.workload, 4, budget_s=25.0, warm_iters=0 if w["cut"] <= 0 else 150)
             line["cpu_baseline"] = {"value": rate, "unit": "it/s", "cores": 1, "kind": kind,
@@ -587,6 +612,11 @@ def main():
                 r2c, kind2, m2 = cpu_reference_rate("C_default", 400, budget_s=15.0, warm_iters=150)
                 secondary["cpu_baseline"] = {"value": r2c, "unit": "it/s", "cores": 1, "kind": kind2,
                                              "sample": f"{m2} sampling iterations after 150 warm-up iterations"}
+            if others:
+                for name, wl_name, warm in (("B_default_cut", "B_default", 150), ("B_full", "B", 0)):
+                    rc_, kind_, m_ = cpu_reference_rate(wl_name, 200, budget_s=8.0, warm_iters=warm)
+                    others[name]["cpu_baseline"] = {"value": rc_, "unit": "it/s", "cores": 1, "kind": kind_,
+                                                    "sample": f"{m_} sampling iterations after {warm} warm-up iterations"}
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

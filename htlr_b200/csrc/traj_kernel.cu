@@ -730,7 +730,9 @@ bool fused_plan(const Geom& g, int smem_optin_bytes, int cl, FusedGeom* out) {
 
 // Largest cluster (16, else 8) that can be resident with this shared-memory footprint, or 0.
 int fused_cluster_size(const Geom& g, int smem_optin_bytes) {
-  for (int cl = kClMax; cl >= 8; cl >>= 1) {
+  int top = kClMax, bottom = 8;
+  if (const char* force = std::getenv("HTLR_CLUSTER_SIZE")) top = bottom = std::atoi(force);   // experiments only
+  for (int cl = top; cl >= bottom; cl >>= 1) {
     FusedGeom fg{};
     if (!fused_plan(g, smem_optin_bytes, cl, &fg)) continue;
     int nclusters = 0;
