@@ -51,7 +51,7 @@ class HtlrProfile(ctypes.Structure):
                 ("sweep_launches", ctypes.c_int64), ("total_ms", ctypes.c_double),
                 ("kernel_launches", ctypes.c_int64), ("sigma_ms", ctypes.c_double),
                 ("fused_sweep_ms", ctypes.c_double), ("fused_barrier_ms", ctypes.c_double),
-                ("fused_rowphase_ms", ctypes.c_double), ("reserved", ctypes.c_double * 1)]
+                ("fused_rowphase_ms", ctypes.c_double), ("small_kernel_trajectories", ctypes.c_double)]
 
 
 TICK_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(HtlrIterStats),

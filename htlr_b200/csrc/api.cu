@@ -67,6 +67,9 @@ struct htlr_handle {
   bool has_cluster = false; // cluster-mode flavour applies (fgc)
   FusedGeom fgc{};
   bool use_cluster = false; // launch the cluster-mode flavour ahead of the grid-mode one
+  bool use_small = false;   // launch the single-block kernel ahead of both
+  int smem_optin = 0;
+  unsigned long long small_base = 0;
   bool profiling = false;
   std::vector<EventPair> ev_pool;
   size_t ev_used = 0;
@@ -192,6 +195,11 @@ int enqueue_step(htlr_handle* h, int L, bool until_energy_only = false) {
   if (h->fused) {
     ProfScope ps(h, 0);
     h->fg.timing = h->fgc.timing = h->profiling ? 1 : 0;
+    if (h->use_small) {
+      // a restricted set that fits in one SM's shared memory: no inter-block exchange at all
+      CU(launch_traj_small(g, b, L, h->smem_optin, 1 << 20, st));
+      ++nk;
+    }
     if (h->use_cluster) {
       // one cluster runs the whole trajectory out of shared memory when the restricted set is small enough
       // (cl_umax); otherwise it leaves traj_done = 0 and the grid-mode launch does the work
@@ -258,7 +266,8 @@ cudaGraphExec_t get_graph(htlr_handle* h, int L) {
 int kernels_per_step(const htlr_handle* h, int L) {
   int per_grad = h->sharded ? 3 : 2;
   int n = 2 + 2 + per_grad + L * (2 + per_grad) + 1 + 1 + 1 + 1;
-  if (h->fused) n = 2 + 2 + 1 + 1 + 1 + 1 + (h->cfg.algo == HTLR_ALGO_CLUSTER_ONLY ? 0 : 1) + (h->use_cluster ? 1 : 0);
+  if (h->fused) n = 2 + 2 + 1 + 1 + 1 + 1 + (h->cfg.algo == HTLR_ALGO_CLUSTER_ONLY ? 0 : 1) + (h->use_cluster ? 1 : 0) +
+                     (h->use_small ? 1 : 0);
   if (h->cfg.ptype == HTLR_PRIOR_T && h->cfg.eta > 1e-10) n += 1;
   return n;
 }
@@ -435,7 +444,7 @@ void do_create(const htlr_cfg* cfg, const double* X, int64_t ldx, const double* 
       FAIL(HTLR_E_ARG, "fused trajectory not applicable (needs K <= 4, a column tile in shared memory, one GPU)");
     h->fused = can && c.algo != HTLR_ALGO_TWO_SWEEP;
     h->fg = fgm;
-    if (h->fused && c.algo != HTLR_ALGO_FUSED) {
+    if (h->fused && c.algo != HTLR_ALGO_FUSED) {   // AUTO, FUSED_CLUSTER, CLUSTER_ONLY, FUSED_NO_SMALL
       const int cl = fused_cluster_size(g, (int)prop.sharedMemPerBlockOptin);
       h->has_cluster = cl > 0 && fused_plan(g, (int)prop.sharedMemPerBlockOptin, cl, &h->fgc);
       if (h->has_cluster) {
@@ -454,6 +463,8 @@ void do_create(const htlr_cfg* cfg, const double* X, int64_t ldx, const double* 
     if ((c.algo == HTLR_ALGO_FUSED_CLUSTER || c.algo == HTLR_ALGO_CLUSTER_ONLY) && !h->has_cluster)
       FAIL(HTLR_E_ARG, "cluster-mode trajectory kernel not available on this device");
     h->use_cluster = h->fused && h->has_cluster;
+    h->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    h->use_small = h->fused && small_applies(g) && (c.algo == HTLR_ALGO_AUTO || c.algo == HTLR_ALGO_CLUSTER_ONLY);
   }
   b.lvpart = h->dalloc<double>((size_t)std::max(g.lv_cs, g.sm_count) * K * g.n_s);
   b.red = h->dalloc<Red4>((size_t)std::max(std::max(g.e_grid, (n + 255) / 256), g.sm_count));
@@ -925,11 +936,13 @@ int htlr_cuda_profile_get(htlr_handle* h, htlr_profile* out, int32_t reset) {
     h->prof.fused_sweep_ms = (double)(c.ph_cycles[0] - h->ph_base[0]) / per_ms;
     h->prof.fused_barrier_ms = (double)(c.ph_cycles[1] - h->ph_base[1] + c.ph_cycles[3] - h->ph_base[3]) / per_ms;
     h->prof.fused_rowphase_ms = (double)(c.ph_cycles[2] - h->ph_base[2]) / per_ms;
+    h->prof.small_kernel_trajectories = (double)(c.small_runs - h->small_base);
     *out = h->prof;
     if (reset) {
       h->prof = htlr_profile{};
       h->cols_base = c.cols_swept;
       for (int q = 0; q < 4; ++q) h->ph_base[q] = c.ph_cycles[q];
+      h->small_base = c.small_runs;
     }
   });
 }

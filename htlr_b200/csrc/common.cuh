@@ -37,6 +37,7 @@ struct Ctl {
   double logw, loglike, loglike_new, loglike_old;
   double nenergy_old, nenergy_new;
   int accept;
+  unsigned long long small_runs;   // trajectories run by the single-block kernel (profiling / tests)
   int traj_done;   // cluster-mode trajectory kernel ran this thin-step (the grid-mode launch then exits)
   double uvar_acc, rej_acc;
   // inject cursors and sizes

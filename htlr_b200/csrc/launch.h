@@ -110,6 +110,10 @@ bool fused_plan(const Geom& g, int smem_optin_bytes, int cl, FusedGeom* out);
 int fused_cluster_size(const Geom& g, int smem_optin_bytes);
 cudaError_t launch_traj_fused(const Geom& g, const Bufs& b, const FusedGeom& fg, int L, cudaStream_t st);
 
+// small_kernel.cu: single-block trajectory for restricted sets that fit in one SM's shared memory
+bool small_applies(const Geom& g);
+cudaError_t launch_traj_small(const Geom& g, const Bufs& b, int L, int smem_bytes, int u_max, cudaStream_t st);
+
 // sigma_kernels.cu (compiled with --fmad=false)
 void launch_sigma(const Geom& g, const Bufs& b, cudaStream_t st);      // t prior: gamma draws
 void launch_sigma_ars(const Geom& g, const Bufs& b, cudaStream_t st);  // ghs / neg: warp-per-feature ARS

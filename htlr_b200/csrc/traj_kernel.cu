@@ -173,6 +173,7 @@ __global__ void __launch_bounds__(kFT, 1) k_traj(Geom g, Bufs b, FusedGeom fg, i
   const int u = ctl->u;
   unsigned* gcounter = &ctl->ticket[4];
   unsigned gen = 0;
+  if (ctl->traj_done) return;   // an earlier launch of this thin-step (single-block or cluster kernel) ran the trajectory
   if (CL) {
     // restricted set too large for one cluster (state capacity, or past the size where grid mode is faster):
     // leave the proposal to the grid-mode launch that follows
@@ -180,8 +181,6 @@ __global__ void __launch_bounds__(kFT, 1) k_traj(Geom g, Bufs b, FusedGeom fg, i
       if (fg.cl_only && cta == 0 && tid == 0) set_err(ctl, kErrClusterCap, u);
       return;
     }
-  } else {
-    if (ctl->traj_done) return;   // the cluster-mode launch before this one already ran the trajectory
   }
   auto sync_all = [&]() {
     if (CL) cluster_barrier(); else grid_barrier(gcounter, gen, G);

@@ -56,11 +56,14 @@ enum { HTLR_RNG_DEVICE = 0, HTLR_RNG_INJECT = 1 };
  *            leapfrog step, for restricted sets of a few hundred columns (falls back to FUSED by itself when
  *            the set is too large). AUTO launches both; the device picks one per iteration from the size of the
  *            restricted set (cluster up to ~3 MB of X[:, iup]).
+ * Ahead of both, AUTO and CLUSTER_ONLY launch a single-block kernel that runs the trajectory
+ * entirely inside one SM (two __syncthreads per leapfrog step) whenever X[:, iup] fits in its shared memory
+ * (a few dozen columns: config A, config B with the default cut); FUSED_NO_SMALL is AUTO without it.
  * CLUSTER_ONLY: FUSED_CLUSTER without the all-SM fallback launch, so that several chains (handles) can run
  *            concurrently on one GPU, each on its own 16-SM cluster (config D: 4 chains / folds per GPU). A
  *            restricted set beyond the cluster's capacity is HTLR_E_SAMPLER. */
 enum { HTLR_ALGO_AUTO = 0, HTLR_ALGO_TWO_SWEEP = 1, HTLR_ALGO_FUSED = 2, HTLR_ALGO_FUSED_CLUSTER = 3,
-       HTLR_ALGO_CLUSTER_ONLY = 4 };
+       HTLR_ALGO_CLUSTER_ONLY = 4, HTLR_ALGO_FUSED_NO_SMALL = 5 };
 
 typedef struct htlr_handle htlr_handle;
 
@@ -115,7 +118,7 @@ typedef struct htlr_profile {
   /* fused trajectory kernel, block 0's view (SM cycle counter / clock rate): time in the column sweeps,
    * waiting at the two grid-wide barriers of each leapfrog step, and in the row phase between them */
   double fused_sweep_ms, fused_barrier_ms, fused_rowphase_ms;
-  double reserved[1];
+  double small_kernel_trajectories;   /* proposals run by the single-block kernel since create / reset */
 } htlr_profile;
 
 /* Replaces `Fit::Fit` + `Fit::Initialize` (gibbs.cpp:4-50, 519-530).

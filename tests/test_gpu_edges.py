@@ -30,7 +30,7 @@ def _chain(args, algo, T=None, tol=1e-8, **kw):
 
 
 ALGOS = [pytest.param(1, id="two-sweep"), pytest.param(2, id="fused"), pytest.param(3, id="cluster"),
-         pytest.param(0, id="auto")]
+         pytest.param(0, id="auto"), pytest.param(4, id="cluster-only")]
 
 
 @pytest.mark.parametrize("algo", ALGOS)
@@ -113,6 +113,23 @@ def test_concurrent_chains_on_one_gpu_match_their_solo_runs():
         for k in ("mcdeltas", "mcsigmasbt", "mcloglike", "mcuvar", "mchmcrej"):
             assert np.array_equal(out[k], solo[c][k]), k
         s.close()
+
+
+def test_auto_uses_the_single_block_kernel_when_the_restricted_set_fits():
+    """AUTO: a restricted set that fits in one SM's shared memory is run by k_traj_small; a large one is not."""
+    import htlr_b200
+    small = problem(300, 40, 3, seed=4, iters_rmc=6, iters_h=2, leap_L=8, hmc_sgmcut=0.0)      # 41 columns, 98 KB
+    big = problem(300, 400, 3, seed=4, iters_rmc=6, iters_h=2, leap_L=8, hmc_sgmcut=0.0)       # 401 columns
+    for args, expect in ((small, 8), (big, 0)):
+        s = htlr_b200.Sampler(**args, seed=2, algo=0)
+        s.profile_get(reset=True)
+        s.run(8)
+        assert s.profile_get()["small_kernel_trajectories"] == expect
+        s.close()
+    s = htlr_b200.Sampler(**small, seed=2, algo=5)     # FUSED_NO_SMALL
+    s.run(8)
+    assert s.profile_get()["small_kernel_trajectories"] == 0
+    s.close()
 
 
 def test_run_past_the_end_is_refused():

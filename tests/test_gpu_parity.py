@@ -50,7 +50,8 @@ def test_initial_state_matches_oracle():
     gpu.close()
 
 
-ALGOS = [pytest.param(1, id="two-sweep"), pytest.param(2, id="fused"), pytest.param(3, id="cluster")]
+ALGOS = [pytest.param(1, id="two-sweep"), pytest.param(2, id="fused"), pytest.param(3, id="cluster"),
+         pytest.param(0, id="auto")]
 
 
 @pytest.mark.parametrize("algo", ALGOS)
@@ -235,7 +236,7 @@ def test_fused_and_two_sweep_chains_agree():
     import htlr_b200
     args = problem(400, 600, 3, seed=31, iters_rmc=6, iters_h=6, leap_L=25)
     outs = []
-    for algo in (1, 2, 3, 0):
+    for algo in (1, 2, 3, 0, 5):
         s = htlr_b200.Sampler(**args, seed=99, algo=algo)
         s.run(5)      # AUTO re-decides grid / cluster mode at every call from the restricted-set size it last saw
         s.run(7)
