@@ -45,6 +45,8 @@ WORKLOADS = {
     "D": dict(gen="mlr", n=200, p=50000, C=2, cut=0.05, seed=1004,
               desc="independent chains of gendata_MLR n=200 p=50000 C=2, t prior df=1, leap=50, htlr() defaults (cut=0.05), "
                    "several chains per GPU running concurrently, no communication"),
+    "A": dict(gen="colon", n=62, p=2000, C=2, cut=0.05, seed=1001,
+              desc="colon (n=62, p=2000, binary), t prior df=1, leap=50, htlr() defaults (cut=0.05)"),
     "tiny": dict(gen="mlr", n=120, p=400, C=3, cut=0.0, seed=5, desc="tiny smoke workload"),
     # config E: ONE chain over all ranks, X row-sharded, NCCL all-reduce of the u x K gradient per leapfrog step
     "E": dict(gen="mlr_device", n=200000, p=10000, C=5, cut=0.0, seed=1005,
@@ -59,6 +61,15 @@ HTLR_DEFAULTS = dict(ptype="t", alpha=1.0, s=-10.0, eta=0.0, thin=1, leap_L=50, 
 def make_problem(wl, chain_seed=0):
     from htlr_b200 import synth
     w = WORKLOADS[wl]
+    if w["gen"] == "colon":
+        # config A: the reference's own data set (data/colon.rda, parsed once into tests/golden/colon.npz by
+        # tests/golden/make_colon.py), prepared as R/core.r:103-146 does
+        d = np.load(os.path.join(ROOT, "tests", "golden", "colon.npz"))
+        Xc, yc = np.asarray(d["X"], dtype=np.float64), d["y"]
+        X, ymat, ybase, K = synth.make_inputs(synth.std_median_sd(Xc), yc)
+        deltas, sig = synth.init_state(w["p"], K, init="zero", seed=w["seed"] + 17 + chain_seed)
+        return dict(p=w["p"], K=K, n=w["n"], X=X, ymat=ymat, ybase=ybase, deltas=deltas, sigmasbt=sig,
+                    hmc_sgmcut=w["cut"], **HTLR_DEFAULTS)
     if w["gen"] == "mlr_device":
         # CPU legs only: a host-generated row subsample of the same law (the reference's cost is linear in n)
         w = dict(w, n=E_CPU_ROWS)
@@ -543,7 +554,7 @@ def main():
         # config B (BASELINE configs[1]) in both regimes, and one whole default run of config C
         # (htlr() defaults: iter = 2000, warmup = 1000) through the public entry point with host buffers
         others = {}
-        for name, wl_name in (("B_default_cut", "B_default"), ("B_full", "B")):
+        for name, wl_name in (("A_colon_default_cut", "A"), ("B_default_cut", "B_default"), ("B_full", "B")):
             rb = measure_workload(torch, wl_name, 200, a.warmup, local, rank, None, want_profile=False)
             others[name] = {"workload": WORKLOADS[wl_name]["desc"], "value": 200 / (rb["ms"] * 1e-3), "unit": "it/s",
                             "ms_per_step": rb["ms"] / 200, "mean_nuvar": rb["uvar"], "hmc_reject": rb["rej"],
@@ -613,7 +624,8 @@ def main():
                 secondary["cpu_baseline"] = {"value": r2c, "unit": "it/s", "cores": 1, "kind": kind2,
                                              "sample": f"{m2} sampling iterations after 150 warm-up iterations"}
             if others:
-                for name, wl_name, warm in (("B_default_cut", "B_default", 150), ("B_full", "B", 0)):
+                for name, wl_name, warm in (("A_colon_default_cut", "A", 150), ("B_default_cut", "B_default", 150),
+                                            ("B_full", "B", 0)):
                     rc_, kind_, m_ = cpu_reference_rate(wl_name, 200, budget_s=8.0, warm_iters=warm)
                     others[name]["cpu_baseline"] = {"value": rc_, "unit": "it/s", "cores": 1, "kind": kind_,
                                                     "sample": f"{m_} sampling iterations after {warm} warm-up iterations"}

@@ -197,7 +197,8 @@ int enqueue_step(htlr_handle* h, int L, bool until_energy_only = false) {
     h->fg.timing = h->fgc.timing = h->profiling ? 1 : 0;
     if (h->use_small) {
       // a restricted set that fits in one SM's shared memory: no inter-block exchange at all
-      CU(launch_traj_small(g, b, L, h->smem_optin, 1 << 20, st));
+      // measured (tools/small_sweep.py): it beats the cluster kernel while u * n <= ~6000 for n <= 256
+      CU(launch_traj_small(g, b, L, h->smem_optin, h->cfg.algo == HTLR_ALGO_SMALL_FIRST ? (1 << 20) : 6000 / g.n, st));
       ++nk;
     }
     if (h->use_cluster) {
@@ -444,7 +445,7 @@ void do_create(const htlr_cfg* cfg, const double* X, int64_t ldx, const double* 
       FAIL(HTLR_E_ARG, "fused trajectory not applicable (needs K <= 4, a column tile in shared memory, one GPU)");
     h->fused = can && c.algo != HTLR_ALGO_TWO_SWEEP;
     h->fg = fgm;
-    if (h->fused && c.algo != HTLR_ALGO_FUSED) {   // AUTO, FUSED_CLUSTER, CLUSTER_ONLY, FUSED_NO_SMALL
+    if (h->fused && c.algo != HTLR_ALGO_FUSED) {   // AUTO, FUSED_CLUSTER, CLUSTER_ONLY, FUSED_NO_SMALL, SMALL_FIRST
       const int cl = fused_cluster_size(g, (int)prop.sharedMemPerBlockOptin);
       h->has_cluster = cl > 0 && fused_plan(g, (int)prop.sharedMemPerBlockOptin, cl, &h->fgc);
       if (h->has_cluster) {
@@ -464,7 +465,9 @@ void do_create(const htlr_cfg* cfg, const double* X, int64_t ldx, const double* 
       FAIL(HTLR_E_ARG, "cluster-mode trajectory kernel not available on this device");
     h->use_cluster = h->fused && h->has_cluster;
     h->smem_optin = (int)prop.sharedMemPerBlockOptin;
-    h->use_small = h->fused && small_applies(g) && (c.algo == HTLR_ALGO_AUTO || c.algo == HTLR_ALGO_CLUSTER_ONLY);
+    h->use_small = h->fused && small_applies(g) &&
+                   (((c.algo == HTLR_ALGO_AUTO || c.algo == HTLR_ALGO_CLUSTER_ONLY) && g.n <= 256) ||
+                    c.algo == HTLR_ALGO_SMALL_FIRST);
   }
   b.lvpart = h->dalloc<double>((size_t)std::max(g.lv_cs, g.sm_count) * K * g.n_s);
   b.red = h->dalloc<Red4>((size_t)std::max(std::max(g.e_grid, (n + 255) / 256), g.sm_count));

@@ -6,9 +6,9 @@
 //
 // Same arithmetic as k_traj (traj_kernel.cu): Fit::Traject, gibbs.cpp:390-419, all L+1 gradient evaluations in one
 // launch, X[:, iup] loaded once (TMA bulk copies) and resident for the whole trajectory.
-//   gradient phase  warp <-> column: lane-strided dot products with the residual (128-bit shared-memory loads),
-//                   xor-shuffle tree, then lane k applies DNlogpost / MoveMomt / UpdateMomtAndDeltas for class k
-//                   and lane 0 forms the next prior-gradient term.
+//   gradient phase  warp <-> 4 columns at a time: lane-strided dot products with the residual (128-bit
+//                   shared-memory loads), interleaved xor-shuffle trees;
+//   update phase    thread <-> column: DNlogpost / MoveMomt / UpdateMomtAndDeltas and the next prior-gradient term;
 //   lv phase        thread <-> (row, column chunk): lv = lv_fix + sum_j X[i, j] delta[j, :] over the chunk's columns
 //                   in ascending order, chunks summed in order, row softmax, residual; log-likelihood at the end.
 // Launched ahead of the cluster-mode and grid-mode kernels; it decides on the device whether the restricted set
@@ -23,6 +23,7 @@ namespace htlr {
 namespace {
 
 constexpr int kST = 512;   // threads
+constexpr int kCI = 4;     // columns a warp reduces at a time in the gradient phase
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -45,14 +46,15 @@ __global__ void __launch_bounds__(kST, 1) k_traj_small(Geom g, Bufs b, int L, in
   if (RPT > kRptMax || u > u_max) return;
   // ---- shared-memory layout (doubles)
   const size_t need = (size_t)u * n_e + (size_t)KT * n_e + (CH > 1 ? (size_t)KT * CH * n32 : 0) +
-                      (size_t)u * (3 * KT + 2) + (size_t)(u + 1) / 2 + 2 * NW + 8;
+                      (size_t)u * (4 * KT + 2) + (size_t)(u + 1) / 2 + 2 * NW + 8;
   if (need > (size_t)smem_doubles) return;       // does not fit: the cluster / grid kernels take the proposal
   extern __shared__ __align__(128) unsigned char sm_raw[];
   double* Xs = reinterpret_cast<double*>(sm_raw);            // [u][n_e]
   double* Rs = Xs + (size_t)u * n_e;                          // [KT][n_e]
   double* part = Rs + (size_t)KT * n_e;                       // [KT][CH][n32] (CH > 1)
   double* st = part + (CH > 1 ? (size_t)KT * CH * n32 : 0);   // [u][3*KT+2]: d, m, prior gradient, sig, step
-  double* red = st + (size_t)u * (3 * KT + 2);                // [2*NW]
+  double* gsm = st + (size_t)u * (3 * KT + 2);                // [u][KT] gradient of the step
+  double* red = gsm + (size_t)u * KT;                         // [2*NW]
   uint64_t* bar = reinterpret_cast<uint64_t*>(red + 2 * NW);  // one mbarrier
   int* cidx = reinterpret_cast<int*>(bar + 1);                // [u]
   constexpr int CS = 3 * KT + 2;
@@ -130,51 +132,69 @@ __global__ void __launch_bounds__(kST, 1) k_traj_small(Geom g, Bufs b, int L, in
 
   double ll_total = 0;
   for (int s = 0; s <= L; ++s) {
-    // ================= gradient + update: warp <-> column =================
-    for (int c = w; c < u; c += NW) {
-      const double* xc = Xs + (size_t)c * n_e;
-      double acc[KT];
+    // ================= gradient: warp <-> kCI columns at a time (independent chains hide the latencies) =========
+    // the warp's kCI columns of a round are NW apart, so few columns still spread over all warps
+    for (int c0 = w; c0 < u; c0 += NW * kCI) {
+      double acc[kCI][KT];
 #pragma unroll
-      for (int k = 0; k < KT; ++k) acc[k] = 0;
+      for (int ci = 0; ci < kCI; ++ci)
+#pragma unroll
+        for (int k = 0; k < KT; ++k) acc[ci][k] = 0;
       for (int m = lane; m < npairs; m += 32) {
-        const double2 x = *reinterpret_cast<const double2*>(xc + 2 * m);
+        double2 r[KT];
 #pragma unroll
-        for (int k = 0; k < KT; ++k) {
-          const double2 r = *reinterpret_cast<const double2*>(Rs + k * n_e + 2 * m);   // pad row holds 0
-          acc[k] = fma(x.x, r.x, fma(x.y, r.y, acc[k]));
+        for (int k = 0; k < KT; ++k) r[k] = *reinterpret_cast<const double2*>(Rs + k * n_e + 2 * m);   // pad row holds 0
+#pragma unroll
+        for (int ci = 0; ci < kCI; ++ci) {
+          if (c0 + NW * ci < u) {
+            const double2 x = *reinterpret_cast<const double2*>(Xs + (size_t)(c0 + NW * ci) * n_e + 2 * m);
+#pragma unroll
+            for (int k = 0; k < KT; ++k) acc[ci][k] = fma(x.x, r[k].x, fma(x.y, r[k].y, acc[ci][k]));
+          }
         }
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-        for (int k = 0; k < KT; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
-      double* sc = st + (size_t)c * CS;
-      if (lane < KT) {
-        double gl = acc[0];
+        for (int ci = 0; ci < kCI; ++ci)
 #pragma unroll
-        for (int k = 1; k < KT; ++k) if (lane == k) gl = acc[k];
-        const double stp = sc[3 * KT + 1], hs = stp / 2;
-        const double dk = sc[lane];
-        double mm = sc[KT + lane];
-        const double post = gl + sc[2 * KT + lane];
+          for (int k = 0; k < KT; ++k) acc[ci][k] += __shfl_xor_sync(0xffffffffu, acc[ci][k], o);
+      if (lane == 0) {
+#pragma unroll
+        for (int ci = 0; ci < kCI; ++ci)
+          if (c0 + NW * ci < u) {
+#pragma unroll
+            for (int k = 0; k < KT; ++k) gsm[(size_t)(c0 + NW * ci) * KT + k] = acc[ci][k];
+          }
+      }
+    }
+    __syncthreads();
+    // ================= update: thread <-> column (DNlogpost, MoveMomt, UpdateMomtAndDeltas, next prior gradient) ====
+    for (int c = tid; c < u; c += kST) {
+      double* sc = st + (size_t)c * CS;
+      const double stp = sc[3 * KT + 1], hs = stp / 2, sig = sc[3 * KT];
+      double dn[KT];
+#pragma unroll
+      for (int k = 0; k < KT; ++k) {
+        const double post = gsm[(size_t)c * KT + k] + sc[2 * KT + k];
         const double kick = __dmul_rn(hs, post);
+        double mm = sc[KT + k];
         if (s >= 1) mm = __dsub_rn(mm, kick);
-        double dnew = dk;
+        double dnew = sc[k];
         if (s < L) {
           mm = __dsub_rn(mm, kick);
-          dnew = __dadd_rn(dk, __dmul_rn(stp, mm));
+          dnew = __dadd_rn(dnew, __dmul_rn(stp, mm));
         }
-        sc[lane] = dnew;
-        sc[KT + lane] = mm;
+        sc[KT + k] = mm;
+        dn[k] = dnew;
       }
-      __syncwarp();
-      if (lane == 0 && s < L) {
-        double sd = sc[0];
+      if (s < L) {
+        double sd = dn[0];
 #pragma unroll
-        for (int k = 1; k < KT; ++k) sd += sc[k];
-        const double sdc = sd / Cd, sig = sc[3 * KT];
+        for (int k = 1; k < KT; ++k) sd += dn[k];
+        const double sdc = sd / Cd;
 #pragma unroll
-        for (int k = 0; k < KT; ++k) sc[2 * KT + k] = (sc[k] - sdc) / sig;
+        for (int k = 0; k < KT; ++k) { sc[k] = dn[k]; sc[2 * KT + k] = (dn[k] - sdc) / sig; }
       }
     }
     __syncthreads();

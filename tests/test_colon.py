@@ -61,7 +61,7 @@ def test_oracle_reproduces_reference_chain_on_colon():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("algo", [pytest.param(1, id="two-sweep"), pytest.param(2, id="fused"),
-                                  pytest.param(3, id="cluster"), pytest.param(0, id="auto")])
+                                  pytest.param(3, id="cluster"), pytest.param(0, id="auto"), pytest.param(6, id="small-first")])
 def test_cuda_reproduces_reference_chain_on_colon(algo):
     import htlr_b200
     d, args, st = colon_case()

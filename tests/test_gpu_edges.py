@@ -30,7 +30,7 @@ def _chain(args, algo, T=None, tol=1e-8, **kw):
 
 
 ALGOS = [pytest.param(1, id="two-sweep"), pytest.param(2, id="fused"), pytest.param(3, id="cluster"),
-         pytest.param(0, id="auto"), pytest.param(4, id="cluster-only")]
+         pytest.param(0, id="auto"), pytest.param(4, id="cluster-only"), pytest.param(6, id="small-first")]
 
 
 @pytest.mark.parametrize("algo", ALGOS)
@@ -118,8 +118,8 @@ def test_concurrent_chains_on_one_gpu_match_their_solo_runs():
 def test_auto_uses_the_single_block_kernel_when_the_restricted_set_fits():
     """AUTO: a restricted set that fits in one SM's shared memory is run by k_traj_small; a large one is not."""
     import htlr_b200
-    small = problem(300, 40, 3, seed=4, iters_rmc=6, iters_h=2, leap_L=8, hmc_sgmcut=0.0)      # 41 columns, 98 KB
-    big = problem(300, 400, 3, seed=4, iters_rmc=6, iters_h=2, leap_L=8, hmc_sgmcut=0.0)       # 401 columns
+    small = problem(100, 40, 3, seed=4, iters_rmc=6, iters_h=2, leap_L=8, hmc_sgmcut=0.0)      # 41 columns x 100 rows
+    big = problem(100, 400, 3, seed=4, iters_rmc=6, iters_h=2, leap_L=8, hmc_sgmcut=0.0)       # 401 columns
     for args, expect in ((small, 8), (big, 0)):
         s = htlr_b200.Sampler(**args, seed=2, algo=0)
         s.profile_get(reset=True)
