@@ -524,6 +524,11 @@ def main():
             dist.destroy_process_group()
         return
 
+    if world > 1:
+        # the CPU baseline and the extra single-GPU blocks belong to the N = 1 line only
+        a.no_cpu_baseline = True
+        a.no_secondary = True
+
     w = WORKLOADS[a.workload]
     clocks = ClockSampler(local)
     clocks.start()

@@ -60,7 +60,7 @@ TICK_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int32, ctypes
 # every symbol include/htlr_cuda.h declares
 EXPORTS = [
     "htlr_cuda_create", "htlr_cuda_destroy", "htlr_cuda_run", "htlr_cuda_fetch", "htlr_cuda_hist_len",
-    "htlr_cuda_fit", "htlr_cuda_summary", "htlr_cuda_predict", "htlr_cuda_eval", "htlr_cuda_trajectory", "htlr_cuda_get_state", "htlr_cuda_ars",
+    "htlr_cuda_fit", "htlr_cuda_summary", "htlr_cuda_predict", "htlr_cuda_std", "htlr_cuda_eval", "htlr_cuda_trajectory", "htlr_cuda_get_state", "htlr_cuda_ars",
     "htlr_cuda_rng_dump", "htlr_cuda_stream", "htlr_cuda_profile_enable", "htlr_cuda_profile_get",
     "htlr_cuda_launch_count", "htlr_cuda_sync", "htlr_cuda_run_async", "htlr_cuda_nccl_unique_id",
     "htlr_cuda_nccl_init", "htlr_cuda_nccl_destroy", "htlr_cuda_last_error", "htlr_cuda_abi_version",
@@ -105,6 +105,8 @@ def lib():
                                     c_dp, c_dp, c_ip]
     L.htlr_cuda_predict.argtypes = [ctypes.c_void_p, c_dp, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
                                     ctypes.c_int32, ctypes.c_int32, c_dp]
+    L.htlr_cuda_std.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64,
+                                ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64, c_dp, c_dp]
     L.htlr_cuda_get_state.argtypes = [ctypes.c_void_p] + [c_dp] * 6
     L.htlr_cuda_eval.argtypes = [ctypes.c_void_p, c_ip, ctypes.c_int32, c_dp, c_dp, c_dp, c_dp, c_dp]
     L.htlr_cuda_trajectory.argtypes = [ctypes.c_void_p, c_dp, ctypes.c_int32, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp,

@@ -912,6 +912,47 @@ int htlr_cuda_predict(htlr_handle* h, const double* X_ts, int64_t ldx, int32_t n
   });
 }
 
+int htlr_cuda_std(int32_t device, int32_t n, int32_t p, const double* A, int64_t lda, int32_t on_device,
+                  double* A_std, int64_t ldo, double* median, double* sd) {
+  return guarded(nullptr, [&] {
+    if (n < 2 || p < 1 || !A || lda < n || (A_std && ldo < n)) FAIL(HTLR_E_ARG, "bad matrix for std");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+      FAIL(HTLR_E_CUDA, "no CUDA device visible: this library has no CPU fallback");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    double *dA = nullptr, *dO = nullptr, *dm = nullptr, *ds = nullptr;
+    auto cleanup = [&] { if (!on_device) { cudaFree(dA); cudaFree(dO); } cudaFree(dm); cudaFree(ds); };
+    try {
+      CU(cudaMalloc((void**)&dm, sizeof(double) * p));
+      CU(cudaMalloc((void**)&ds, sizeof(double) * p));
+      const double* src = A;
+      double* dst = A_std;
+      int64_t ls = lda, ld = ldo;
+      if (!on_device) {
+        CU(cudaMalloc((void**)&dA, sizeof(double) * (size_t)n * p));
+        CU(cudaMemcpy2D(dA, (size_t)n * sizeof(double), A, (size_t)lda * sizeof(double), (size_t)n * sizeof(double), p,
+                        cudaMemcpyHostToDevice));
+        src = dA; ls = n;
+        if (A_std) { CU(cudaMalloc((void**)&dO, sizeof(double) * (size_t)n * p)); dst = dO; ld = n; }
+      }
+      launch_std(n, p, src, ls, dst, ld, dm, ds, prop.multiProcessorCount, 0);
+      CU(cudaDeviceSynchronize());
+      CU(cudaGetLastError());
+      if (!on_device && A_std)
+        CU(cudaMemcpy2D(A_std, (size_t)ldo * sizeof(double), dO, (size_t)n * sizeof(double), (size_t)n * sizeof(double), p,
+                        cudaMemcpyDeviceToHost));
+      if (median) CU(cudaMemcpy(median, dm, sizeof(double) * p, cudaMemcpyDeviceToHost));
+      if (sd) CU(cudaMemcpy(sd, ds, sizeof(double) * p, cudaMemcpyDeviceToHost));
+    } catch (...) {
+      cleanup();
+      throw;
+    }
+    cleanup();
+  });
+}
+
 void* htlr_cuda_stream(htlr_handle* h) { return h ? (void*)h->st : nullptr; }
 
 int htlr_cuda_profile_enable(htlr_handle* h, int32_t on) {

@@ -110,6 +110,10 @@ bool fused_plan(const Geom& g, int smem_optin_bytes, int cl, FusedGeom* out);
 int fused_cluster_size(const Geom& g, int smem_optin_bytes);
 cudaError_t launch_traj_fused(const Geom& g, const Bufs& b, const FusedGeom& fg, int L, cudaStream_t st);
 
+// std_kernels.cu: std_helper (src/utils.cpp:36-48) on device-resident column-major data; out may be null or == A
+void launch_std(int n, int p, const double* A, int64_t lda, double* out, int64_t ldo, double* med, double* sd,
+                int sm_count, cudaStream_t st);
+
 // small_kernel.cu: single-block trajectory for restricted sets that fit in one SM's shared memory
 bool small_applies(const Geom& g);
 cudaError_t launch_traj_small(const Geom& g, const Bufs& b, int L, int smem_bytes, int u_max, cudaStream_t st);

@@ -293,3 +293,16 @@ def rng_dump(seed, purpose, step, n_a, n_b, kind, shape=1.0, device=0):
     if rc:
         raise HtlrCudaError(rc, L.htlr_cuda_last_error(None).decode())
     return out
+
+
+def std(A, device=0):
+    """`std_helper` (src/utils.cpp:36-48) on the GPU: returns {"median", "sd", "X"} for an n x p matrix."""
+    L = _lib.lib()
+    A = _f64(A, "F")
+    n, p = A.shape
+    out = np.zeros((n, p), order="F")
+    med, sd = np.zeros(p), np.zeros(p)
+    rc = L.htlr_cuda_std(device, n, p, A.ctypes.data, n, 0, out.ctypes.data, n, _ptr(med), _ptr(sd))
+    if rc:
+        raise HtlrCudaError(rc, L.htlr_cuda_last_error(None).decode())
+    return {"median": med, "sd": sd, "X": out}

@@ -170,6 +170,12 @@ int htlr_cuda_summary(htlr_handle* h, int32_t first, int32_t last, int32_t thin,
 int htlr_cuda_predict(htlr_handle* h, const double* X_ts, int64_t ldx, int32_t n_ts, int32_t first, int32_t last,
                       int32_t thin, double* probs);
 
+/* `std_helper` (src/utils.cpp:36-48) on the GPU: column medians, column sample standard deviations (n - 1) and
+ * A_std = (A - median) / sd for column-major n x p data. on_device = 1: A and A_std are device pointers (A_std may
+ * equal A or be NULL); median / sd (length p, host) may be NULL. Exact medians (radix selection). */
+int htlr_cuda_std(int32_t device, int32_t n, int32_t p, const double* A, int64_t lda, int32_t on_device,
+                  double* A_std, int64_t ldo, double* median, double* sd);
+
 /* ---- deterministic pieces, for the parity gate (level 1 of north_star) ---- */
 
 /* lv = X[:,iup] * deltas[iup,:] (nothing fixed), row-softmax, log-likelihood and gradient over iup:

@@ -129,3 +129,19 @@ def test_device_prediction_matches_reference_formulas(n, p, C):
     pr = np.exp(full - np.log(np.exp(full).sum(1, keepdims=True)))[:, 1:].mean(2)
     assert relerr(a2[:, 1:], pr) < 1e-11
     s.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,p", [(62, 300), (63, 17), (2, 5), (1000, 40), (4097, 3)])
+def test_device_std_matches_std_helper(n, p):
+    """htlr_cuda_std against the restatement of std_helper (src/utils.cpp:36-48): exact medians, sample sd."""
+    import htlr_b200
+    g = np.random.default_rng(n + p)
+    A = g.standard_normal((n, p)) * g.uniform(0.5, 5, p) + g.uniform(-3, 3, p)
+    A[::7] = np.round(A[::7], 1)          # ties
+    if n > 10:
+        A[3, 0] = A[5, 0] = A[8, 0]       # repeated values around the middle
+    out = htlr_b200.std(A)
+    assert np.array_equal(out["median"], np.median(A, axis=0))
+    assert relerr(out["sd"], A.std(axis=0, ddof=1)) < 1e-13
+    assert relerr(out["X"], synth.std_median_sd(A)) < 1e-12
