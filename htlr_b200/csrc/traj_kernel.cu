@@ -54,7 +54,8 @@ constexpr int kCW = 16;                 // compute warps
 constexpr int kCT = kCW * 32;           // compute threads
 constexpr int kFT = kCT;                // every warp computes; TMA copies are issued by the groups themselves
 constexpr int kNlpMax = 2;              // row pairs per compute thread when publishing the lv partial (n <= 2048)
-constexpr int kPartSlots = 5;           // lv partials one lane sums in the row phase: grids of up to 160 blocks
+constexpr int kPartSlots = 5;           // grids of up to 160 blocks (32 * kPartSlots)
+constexpr int kWriterSlots = 10;        // publishing blocks one warp covers in the row phase: 16 * 10 = 160
 constexpr int kClMax = 16;              // largest cluster (non-portable size; 8 is the portable fallback)
 constexpr int kNsMax = 64;              // ring stages (one column each)
 constexpr int kBarGroup = 1;            // named barriers 1..4: the compute groups
@@ -159,7 +160,8 @@ __global__ void __launch_bounds__(kFT, 1) k_traj(Geom g, Bufs b, FusedGeom fg, i
   double* lasm = dnsm + 2 * NG * VP;                                         // [KT][n_e] one group's lv partial in transit (NG > 1)
   double* redsm = lasm + (NG > 1 ? (size_t)KT * n_e : 0);                    // [kCW]
   double* dl = redsm + kCW;                                                  // [rpc*KT]
-  double* rowc = dl + ((fg.rpc * KT + 1) & ~1);                              // [rpc][2*KT+2] lv_fix, ymat, label
+  double* wsum = dl + ((fg.rpc * KT + 1) & ~1);                              // [kCW][rpc*KT] per-warp sums of the partials (grid mode)
+  double* rowc = wsum + (CL ? 0 : (size_t)kCW * fg.rpc * KT);                // [rpc][2*KT+2] lv_fix, ymat, label
   double* cst = rowc + (size_t)fg.rpc * (2 * KT + 2);                        // [ncmax][CS]
   double* lp_own = cst + (((size_t)fg.ncmax * CS + 1) & ~(size_t)1);         // cluster mode: own lv partial [KT][n_e]
   double* Rs = lp_own + (CL ? (size_t)KT * n_e : 0);                         // cluster mode: residual copy [KT][n_e]
@@ -318,9 +320,10 @@ __global__ void __launch_bounds__(kFT, 1) k_traj(Geom g, Bufs b, FusedGeom fg, i
             r0v = rr.x;
             r1v = rr.y;
           } else {
-            const double* Rk = b.R + (int64_t)k * n_s + roff[m];
-            r0v = __ldcg(Rk);
-            r1v = (roff[m] + 1 < n) ? __ldcg(Rk + 1) : 0.0;   // pad row of an odd n contributes nothing
+            // 16-byte load; the pad row of an odd n holds 0 in R (never written)
+            const double2 rr = __ldcg(reinterpret_cast<const double2*>(b.R + (int64_t)k * n_s + roff[m]));
+            r0v = rr.x;
+            r1v = rr.y;
           }
         }
         Rg[m][0][k] = r0v;
@@ -514,22 +517,43 @@ __global__ void __launch_bounds__(kFT, 1) k_traj(Geom g, Bufs b, FusedGeom fg, i
           }
         }
       } else {
-        // one (row, class) item per warp pass; all of a lane's partials are requested before any is summed,
-        // so the pass costs one L2 round trip instead of one per 32 blocks
-        for (int item = w; item < nrows * KT; item += kCW) {
-          const int ii = item / KT, k = item - ii * KT;
-          const double* src = b.lvpart + (int64_t)k * n_s + row0 + ii;
-          double pv[kPartSlots];
+        // lane <-> (row, class) item of this block's row slice, warp <-> every 16th publishing block: one warp
+        // instruction reads the block's whole slice of one partial (contiguous rows: full sectors, each fetched
+        // once), a lane has all its loads in flight before the first add; per-warp sums go through shared memory
+        // and are added in warp order. Fixed order throughout: deterministic.
+        {
+          const int nitems = nrows * KT;
+          double a = 0;
+          if (lane < nitems) {
+            const int k = lane / nrows, ii = lane - k * nrows;
+            const double* src = b.lvpart + (int64_t)k * n_s + row0 + ii;
+            double pv[kWriterSlots];
 #pragma unroll
-          for (int qq = 0; qq < kPartSlots; ++qq) {
-            const int sl = lane + 32 * qq;
-            pv[qq] = (sl < gact) ? __ldcg(src + (int64_t)sl * KT * n_s) : 0.0;
+            for (int qq = 0; qq < kWriterSlots; ++qq) {
+              const int sl = w + kCW * qq;
+              pv[qq] = (sl < gact) ? __ldcg(src + (int64_t)sl * KT * n_s) : 0.0;
+            }
+            a = pv[0];
+#pragma unroll
+            for (int qq = 1; qq < kWriterSlots; ++qq) a += pv[qq];
           }
-          double a = pv[0];
+          // items beyond one warp's lanes (more than 32 (row, class) pairs per block: small grids only)
+          for (int item = lane + 32; item < nitems; item += 32) {
+            const int k = item / nrows, ii = item - k * nrows;
+            const double* src = b.lvpart + (int64_t)k * n_s + row0 + ii;
+            double t = 0;
+            for (int sl = w; sl < gact; sl += kCW) t += __ldcg(src + (int64_t)sl * KT * n_s);
+            wsum[(size_t)w * fg.rpc * KT + item] = t;
+          }
+          if (lane < nitems) wsum[(size_t)w * fg.rpc * KT + lane] = a;
+        }
+        named_bar(kBarCompute, kCT);
+        if (ct < nrows * KT) {
+          double t = wsum[ct];
 #pragma unroll
-          for (int qq = 1; qq < kPartSlots; ++qq) a += pv[qq];
-          a = warp_sum(a);
-          if (lane == 0) dl[ii * KT + k] = a;
+          for (int ww = 1; ww < kCW; ++ww) t += wsum[(size_t)ww * fg.rpc * KT + ct];
+          const int k = ct / nrows, ii = ct - k * nrows;
+          dl[ii * KT + k] = t;
         }
         named_bar(kBarCompute, kCT);
         if (ct < nrows) {
@@ -707,7 +731,8 @@ bool fused_plan(const Geom& g, int smem_optin_bytes, int cl, FusedGeom* out) {
   if (cl > 0) ncmax = (int)(24 * 1024 / ((3 * K + 2) * sizeof(double) + sizeof(int))) & ~7;   // columns per block the
                                                                        // cluster keeps state for (24 KB)
   else ncmax = (g.nvar + G - 1) / G + 1;   // worst case: every feature in the restricted set
-  const size_t other = (size_t)(2 * kCW * 8 + 2 * kCW * 8 + kCW + ((rpc * K + 1) & ~1) + rpc * (2 * K + 2) + 2) * sizeof(double) +
+  const size_t other = (size_t)(2 * kCW * 8 + 2 * kCW * 8 + kCW + ((rpc * K + 1) & ~1) + rpc * (2 * K + 2) + 2 +
+                                (cl > 0 ? 0 : kCW * rpc * K)) * sizeof(double) +
                        (ng > 1 ? (size_t)K * n_e * sizeof(double) : 0) +
                        (size_t)ncmax * ((3 * K + 2) * sizeof(double) + sizeof(int)) +
                        (cl > 0 ? (size_t)2 * K * n_e * sizeof(double) : 0) + 2 * kNsMax * sizeof(uint64_t) + 256;
