@@ -225,6 +225,13 @@ int enqueue_step(htlr_handle* h, int L, bool until_energy_only = false) {
   }
   launch_energy(g, b, h->sharded ? 1 : 0, st); ++nk;
   if (until_energy_only) return nk;
+  if (h->cfg.ptype == HTLR_PRIOR_T && !(h->cfg.eta > 1e-10)) {
+    // the default prior: commit, the gamma draws and the trace recording are one per-feature kernel
+    ProfScope ps(h, 2);
+    launch_tail_t(g, b, st); ++nk;
+    CU(cudaGetLastError());
+    return nk;
+  }
   launch_commit(g, b, st); ++nk;
   {
     ProfScope ps(h, 2);
@@ -270,6 +277,7 @@ int kernels_per_step(const htlr_handle* h, int L) {
   if (h->fused) n = 2 + 2 + 1 + 1 + 1 + 1 + (h->cfg.algo == HTLR_ALGO_CLUSTER_ONLY ? 0 : 1) + (h->use_cluster ? 1 : 0) +
                      (h->use_small ? 1 : 0);
   if (h->cfg.ptype == HTLR_PRIOR_T && h->cfg.eta > 1e-10) n += 1;
+  if (h->cfg.ptype == HTLR_PRIOR_T && !(h->cfg.eta > 1e-10)) n -= 2;
   return n;
 }
 
@@ -376,11 +384,11 @@ void do_create(const htlr_cfg* cfg, const double* X, int64_t ldx, const double* 
   {
     // everything create allocates, in one chunk (upper bound of the dalloc calls below + alignment slack)
     const size_t Hh = (size_t)c.iters_rmc + 1 + (c.keep_warmup_hist ? c.iters_h : 0);
-    const size_t nkk = (size_t)g.n_s * K, nv = (size_t)nvar;
+    const size_t nkk = (size_t)g.n_s * K, nv = (size_t)nvar + 64;   // (+64: one more int array than doubles counted)
     size_t dbl = (c.x_on_device ? 0 : (size_t)round_up(n, 16) * nv) + nkk + nv + nv * K + 2 * nv + 4 * nkk +
                  2 * nv * K + 3 * nv + nv * K + 1 + (size_t)g.g_rt * nv * K +
                  (size_t)std::max(g.lv_cs, g.sm_count) * K * g.n_s + Hh * (nv * (K + 2) + 4);
-    size_t bytes = dbl * sizeof(double) + ((size_t)n + 2 * nv) * sizeof(int) + nv +
+    size_t bytes = dbl * sizeof(double) + ((size_t)n + 3 * nv) * sizeof(int) + nv +
                    ((size_t)std::max(std::max(g.e_grid, (n + 255) / 256), g.sm_count) + c.iters_h + c.iters_rmc) * sizeof(Red4) +
                    sizeof(Ctl) + 64 * 256;
     h->arena_reserve(bytes);
@@ -428,6 +436,7 @@ void do_create(const htlr_cfg* cfg, const double* X, int64_t ldx, const double* 
   b.R = h->dalloc<double>(nk);
   b.iup = h->dalloc<int>(nvar);
   b.ifix = h->dalloc<int>(nvar);
+  b.posof = h->dalloc<int>(nvar);
   b.dc = h->dalloc<double>((size_t)nvar * K);
   b.momt = h->dalloc<double>((size_t)nvar * K);
   b.stepc = h->dalloc<double>(nvar);

@@ -56,6 +56,7 @@ struct Bufs {
   double *lv, *lv_old, *lv_fix, *R;         // [k][i], stride n_s (class columns 1..K; class 0 is 0)
   // restricted set + compact per-feature work arrays (index r = position in iup)
   int *iup, *ifix;
+  int* posof;           // inverse map: position of feature j in iup, or -1 (written by k_select)
   double *dc, *momt, *stepc, *sigc, *vdc;   // u x K, u x K, u, u, u
   double* g;            // gradient, u x K (+1 trailing slot for the local log-likelihood when sharded)
   double* gpart;        // [g_rt][nvar*K] partials when g_rt > 1
@@ -120,6 +121,7 @@ cudaError_t launch_traj_small(const Geom& g, const Bufs& b, int L, int smem_byte
 
 // sigma_kernels.cu (compiled with --fmad=false)
 void launch_sigma(const Geom& g, const Bufs& b, cudaStream_t st);      // t prior: gamma draws
+void launch_tail_t(const Geom& g, const Bufs& b, cudaStream_t st);     // t prior, eta = 0: commit + sigma + record in one
 void launch_sigma_ars(const Geom& g, const Bufs& b, cudaStream_t st);  // ghs / neg: warp-per-feature ARS
 void launch_logw(const Geom& g, const Bufs& b, cudaStream_t st);
 void launch_ars_standalone(int kind, int m, const double* vard, double K, double alpha, double log_aw,

@@ -99,8 +99,8 @@ __global__ void __launch_bounds__(1024) k_select(Geom g, Bufs b) {
     const bool f = in && b.sigmasbt[j] > cut;
     const unsigned mu = __ballot_sync(0xffffffffu, f), mf = __ballot_sync(0xffffffffu, in && !f);
     const unsigned below = (1u << lane) - 1u;
-    if (f) b.iup[pu + __popc(mu & below)] = j;
-    else if (in) b.ifix[pf + __popc(mf & below)] = j;
+    if (f) { const int r = pu + __popc(mu & below); b.iup[r] = j; b.posof[j] = r; }
+    else if (in) { b.ifix[pf + __popc(mf & below)] = j; b.posof[j] = -1; }
     pu += __popc(mu);
     pf += __popc(mf);
   }

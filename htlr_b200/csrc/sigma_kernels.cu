@@ -34,6 +34,90 @@ __global__ void __launch_bounds__(256) k_sigma_t(Geom g, Bufs b) {
   }
 }
 
+// t prior, eta = 0 (the htlr() default): the three per-feature kernels that end a thin-step in ONE launch —
+//   commit  keep the proposal (gather through the inverse map posof) or RestoreOldValues   gibbs.cpp:89-95, 493-501
+//   sigma   UpdateSigmasT                                                                    gibbs.cpp:311-331
+//   record  trace slice + per-iteration scalars + cursor bookkeeping                         gibbs.cpp:100-114
+// Thread <-> feature, so a feature's committed coefficients / variance are still in registers when its sigma is
+// drawn and its trace entries are written.
+__global__ void __launch_bounds__(256) k_tail_t(Geom g, Bufs b) {
+  Ctl* ctl = b.ctl;
+  const int nvar = g.nvar, K = g.K, p = ctl->p;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  const bool accept = ctl->accept != 0;
+  const double shape = (ctl->alpha + ctl->K) / 2;
+  const double w = exp(ctl->logw);
+  const KeyedRng rng{ctl->seed};
+  const bool last_thin = (ctl->i_thin == ctl->thin - 1);
+  const int i_rmc = ctl->keep_warmup_hist ? (ctl->i_mc + 1) : (ctl->i_mc - ctl->iters_h + 1);
+  const bool rec = last_thin && i_rmc > 0;
+  double* md = b.mcdeltas + (int64_t)(rec ? i_rmc : 0) * nvar * K;
+  double* ms = b.mcsigmasbt + (int64_t)(rec ? i_rmc : 0) * nvar;
+  double* mv = b.mcvardeltas + (int64_t)(rec ? i_rmc : 0) * nvar;
+  for (int j = tid; j < nvar; j += nt) {
+    const int r = b.posof[j];
+    double vd = b.var_deltas[j];
+    if (accept && r >= 0) {
+      vd = b.vdc[r];
+      b.var_deltas[j] = vd;
+      for (int k = 0; k < K; ++k) {
+        const double d = b.dc[(int64_t)r * K + k];
+        b.deltas[(int64_t)k * nvar + j] = d;
+        if (rec) md[(int64_t)k * nvar + j] = d;
+      }
+    } else if (rec) {
+      for (int k = 0; k < K; ++k) md[(int64_t)k * nvar + j] = b.deltas[(int64_t)k * nvar + j];
+    }
+    double sg = b.sigmasbt[j];
+    if (j >= 1) {
+      double gm;
+      if (ctl->rng_mode == 1) {
+        const long long at = ctl->cur_gam + (j - 1);
+        if (at >= ctl->n_gam) { set_err(ctl, kErrInjectGammas, 0); gm = 1.0; }
+        else gm = b.inj_gam[at];
+      } else {
+        gm = rng.gamma(ctl->step, (uint32_t)j, shape);
+      }
+      sg = (1.0 / gm * (ctl->alpha * w + vd) / 2.0);
+      b.sigmasbt[j] = sg;
+    }
+    if (rec) { ms[j] = sg; mv[j] = vd; }
+  }
+  if (!accept) {
+    const int64_t tot = (int64_t)K * g.n_s;
+    for (int64_t e = tid; e < tot; e += nt) b.lv[e] = b.lv_old[e];
+  }
+  if (last_block(&ctl->ticket[3], gridDim.x)) {
+    if (threadIdx.x == 0) {
+      if (accept) ctl->loglike = ctl->loglike_new;
+      // advance inject cursors (reference consumption: u*K normals, 1 uniform, p gammas per thin-step)
+      ctl->cur_norm += (long long)ctl->u * K;
+      ctl->cur_unif += 1;
+      ctl->cur_gam += p;
+      ctl->step += 1;
+      ctl->step_in_call += 1;
+      if (last_thin) {
+        const double uv = ctl->uvar_acc / ctl->thin, rj = ctl->rej_acc / ctl->thin;
+        if (i_rmc > 0) {
+          b.mclogw[i_rmc] = ctl->logw;
+          b.mcloglike[i_rmc] = ctl->loglike;
+          b.mcuvar[i_rmc] = uv;
+          b.mchmcrej[i_rmc] = rj;
+        }
+        Red4 st;
+        st.a = ctl->loglike; st.b = ctl->logw; st.c = uv; st.d = rj;
+        b.stats[ctl->i_mc] = st;
+        ctl->uvar_acc = 0;
+        ctl->rej_acc = 0;
+        ctl->i_thin = 0;
+        ctl->i_mc += 1;
+      } else {
+        ctl->i_thin += 1;
+      }
+    }
+  }
+}
+
 // ghs / neg: one warp per feature, ARS on x = log sigma^2_j from x0 = log(var_deltas_j / K).
 __global__ void __launch_bounds__(256) k_sigma_ars(Geom g, Bufs b) {
   Ctl* ctl = b.ctl;
@@ -174,6 +258,7 @@ void launch_sigma(const Geom& g, const Bufs& b, cudaStream_t st) {
   // ptype is fixed for the life of the handle; the host picks the kernel
   k_sigma_t<<<g.e_grid, 256, 0, st>>>(g, b);
 }
+void launch_tail_t(const Geom& g, const Bufs& b, cudaStream_t st) { k_tail_t<<<g.e_grid, 256, 0, st>>>(g, b); }
 void launch_sigma_ars(const Geom& g, const Bufs& b, cudaStream_t st) {
   const int p = g.nvar - 1;
   int blocks = (p + 7) / 8;
