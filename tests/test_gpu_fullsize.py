@@ -1,0 +1,85 @@
+"""Size-independent properties at BASELINE.json's full sizes (config C: n = 1000, p = 20000, C = 3), where the CPU
+oracle would take minutes: leapfrog reversibility, agreement of the independent trajectory algorithms, and
+linearity of the deterministic pieces."""
+import numpy as np
+import pytest
+
+from htlr_b200 import synth
+from tests.helpers import DEFAULTS, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def config_c():
+    d = synth.gendata_fam(1000, 20000, sd_g=0.5, stdx=True, seed=1003)
+    X, ymat, ybase, K = synth.make_inputs(d["X"], d["y"])
+    g = np.random.default_rng(5)
+    deltas = np.asfortranarray(g.standard_normal((20001, K)) * 0.02)
+    v = synth.comp_vardeltas(deltas)[1:]
+    sig = np.r_[2000.0, (np.exp(-10.0) + v) / 2 / g.gamma((1 + K) / 2, size=20000)]
+    args = dict(DEFAULTS)
+    args.update(p=20000, K=K, n=1000, X=X, ymat=ymat, ybase=ybase, ptype="t", deltas=deltas, sigmasbt=sig,
+                iters_rmc=3, iters_h=0, leap_L=50, leap_step=0.02)
+    return args
+
+
+@pytest.mark.parametrize("cut", [0.0, 0.05])
+def test_trajectory_algorithms_agree_at_full_size(config_c, cut):
+    """Two-sweep (reference structure) vs the fused kernels: same proposal to rounding, 50 leapfrog steps."""
+    import htlr_b200
+    args = dict(config_c, hmc_sgmcut=cut)
+    g = np.random.default_rng(2)
+    momt = np.asfortranarray(g.standard_normal((20001, args["K"])))
+    outs = []
+    for algo in (1, 2, 3):
+        s = htlr_b200.Sampler(**args, algo=algo)
+        outs.append(s.trajectory(momt, 50))
+        s.close()
+    assert outs[0]["nuvar"] == outs[1]["nuvar"] == outs[2]["nuvar"]
+    assert outs[0]["nuvar"] == (20001 if cut == 0.0 else int((args["sigmasbt"] > cut * cut).sum()))
+    for o in outs[1:]:
+        assert relerr(o["deltas"], outs[0]["deltas"]) < 1e-9
+        assert relerr(o["lv"], outs[0]["lv"]) < 1e-9
+        assert abs(o["nenergy_new"] - outs[0]["nenergy_new"]) < 1e-9 * abs(outs[0]["nenergy_new"])
+        assert abs(o["loglike"] - outs[0]["loglike"]) < 1e-9 * abs(outs[0]["loglike"])
+
+
+def test_leapfrog_is_reversible_at_full_size(config_c):
+    """Leapfrog is time-reversible: run L steps, flip the momenta, run L steps from the proposal: back at the start."""
+    import htlr_b200
+    args = dict(config_c, hmc_sgmcut=0.0)
+    g = np.random.default_rng(3)
+    momt = np.asfortranarray(g.standard_normal((20001, args["K"])))
+    s = htlr_b200.Sampler(**args)
+    fwd = s.trajectory(momt, 30)
+    s.close()
+    back_args = dict(args, deltas=fwd["deltas"])
+    s = htlr_b200.Sampler(**back_args)
+    back = s.trajectory(np.asfortranarray(-fwd["momt"]), 30)
+    s.close()
+    assert relerr(back["deltas"], args["deltas"]) < 1e-9
+    assert relerr(-back["momt"], momt) < 1e-9
+    # and the energy error of the trajectory is small for this step size (symplectic integrator)
+    assert abs(fwd["nenergy_new"] - fwd["nenergy_old"]) < 0.5 * 50
+
+
+def test_linear_predictor_and_gradient_are_linear_at_full_size(config_c):
+    """lv(a d1 + b d2) = a lv(d1) + b lv(d2); the gradient at delta = 0 is X'(1/C - Y) exactly computable per column."""
+    import htlr_b200
+    args = dict(config_c, hmc_sgmcut=0.0)
+    s = htlr_b200.Sampler(**args)
+    g = np.random.default_rng(4)
+    K = args["K"]
+    iup = np.arange(20001, dtype=np.int32)
+    d1 = np.asfortranarray(g.standard_normal((20001, K)) * 0.01)
+    d2 = np.asfortranarray(g.standard_normal((20001, K)) * 0.01)
+    e1, e2, e3 = s.eval(iup, d1), s.eval(iup, d2), s.eval(iup, np.asfortranarray(2.0 * d1 - 3.0 * d2))
+    assert relerr(e3["lv"], 2.0 * e1["lv"] - 3.0 * e2["lv"]) < 1e-11
+    z = s.eval(iup, np.zeros((20001, K), order="F"))
+    assert np.allclose(z["pred"], 1.0 / (K + 1), atol=1e-15)
+    assert abs(z["loglike"] + 1000 * np.log(K + 1)) < 1e-9
+    resid = 1.0 / (K + 1) - args["ymat"]
+    sub = g.choice(20001, 64, replace=False)
+    assert relerr(z["grad"][sub], args["X"][:, sub].T @ resid) < 1e-11
+    s.close()
