@@ -215,6 +215,9 @@ __global__ void __launch_bounds__(kFT, 1) k_traj(Geom g, Bufs b, FusedGeom fg, i
 #pragma unroll
     for (int k = 0; k < KT; ++k) st[2 * KT + k] = (st[k] - sdc) / sig;
   };
+  // the ring starts as zeros (the unconditional tile reads below rely on every stage holding finite values)
+  for (size_t e = tid; e < (size_t)NG * SG * TC * n_e; e += kFT) ring[e] = 0.0;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy zeros before the TMA writes
   // this block's column indices and per-column state live in shared memory for the whole trajectory
   for (int e = tid; e < ncols; e += kFT) {
     const int r = c0 + e;
@@ -343,14 +346,14 @@ __global__ void __launch_bounds__(kFT, 1) k_traj(Geom g, Bufs b, FusedGeom fg, i
       const int buf = tcount & 1;
       if (!resident || s == 0) mbar_wait(&gfull[stage], fph);
       const double* tile = gring + (size_t)stage * TC * n_e;
-      // ---- the thread's rows of every column of the tile: the only shared-memory read of X
+      // ---- the thread's rows of every column of the tile: the only shared-memory read of X. Unconditional:
+      // the ring was zero-filled, so a stage only ever holds X values or zeros; a row pair past the end reads
+      // pair 0 and meets a zero residual, a column past the block's last one meets a zero coefficient below.
       double2 x[TC][NRP];
 #pragma unroll
       for (int c = 0; c < TC; ++c)
 #pragma unroll
-        for (int m = 0; m < NRP; ++m)
-          x[c][m] = (rval[m] && c < nc) ? *reinterpret_cast<const double2*>(tile + c * n_e + roff[m])
-                                        : make_double2(0.0, 0.0);
+        for (int m = 0; m < NRP; ++m) x[c][m] = *reinterpret_cast<const double2*>(tile + c * n_e + roff[m]);
       // ---- gradient partials of the tile (two independent chains per value)
       double vals[VP];
 #pragma unroll
@@ -425,15 +428,13 @@ __global__ void __launch_bounds__(kFT, 1) k_traj(Geom g, Bufs b, FusedGeom fg, i
       if (s < L) {
 #pragma unroll
         for (int c = 0; c < TC; ++c) {
-          if (c < nc) {
 #pragma unroll
-            for (int k = 0; k < KT; ++k) {
-              const double dnk = dnb[c * KT + k];
+          for (int k = 0; k < KT; ++k) {
+            const double dnk = dnb[c * KT + k];   // 0 for a column past the block's last one
 #pragma unroll
-              for (int m = 0; m < NRP; ++m) {
-                la[m][0][k] = fma(x[c][m].x, dnk, la[m][0][k]);
-                la[m][1][k] = fma(x[c][m].y, dnk, la[m][1][k]);
-              }
+            for (int m = 0; m < NRP; ++m) {
+              la[m][0][k] = fma(x[c][m].x, dnk, la[m][0][k]);
+              la[m][1][k] = fma(x[c][m].y, dnk, la[m][1][k]);
             }
           }
         }
