@@ -90,6 +90,7 @@ def test_trajectory_matches_oracle(n, p, C, L, cut, algo):
     dict(n=80, p=60, C=4, thin=1, keep_warmup_hist=True, hmc_sgmcut=0.0),
     dict(n=70, p=90, C=3, thin=1, keep_warmup_hist=False, leap_step=0.9),   # plenty of rejections
     dict(n=64, p=70, C=2, thin=1, keep_warmup_hist=True, eta=0.5),           # logw ARS
+    dict(n=66, p=50, C=3, thin=1, keep_warmup_hist=True, eta=0.005, s=-8.0), # 1e-10 < eta < 0.01: logw = s (gibbs.cpp:337-340)
 ])
 @pytest.mark.parametrize("algo", ALGOS)
 @pytest.mark.parametrize("use_graph", [False, True])
