@@ -462,9 +462,9 @@ void do_create(const htlr_cfg* cfg, const double* X, int64_t ldx, const double* 
         // launched and the one that is not wanted returns at once (~2.5 us). Grid mode (148 blocks, exchange
         // through L2) is bandwidth efficient; cluster mode (one cluster, exchange through shared memory,
         // hardware barriers) has lower latency per leapfrog step but a fraction of the bandwidth: measured
-        // crossover at about 3 MB of X[:, iup] (tools/mode_sweep.py).
+        // crossover at about 1.5 MB of X[:, iup] (tools/mode_sweep.py).
         const int cap = h->fgc.cl * h->fgc.ncmax;
-        const int by_bytes = (int)std::min<double>(3.0e6 / (8.0 * n), 2.0e9);
+        const int by_bytes = (int)std::min<double>(1.5e6 / (8.0 * n), 2.0e9);
         const bool forced = c.algo == HTLR_ALGO_FUSED_CLUSTER || c.algo == HTLR_ALGO_CLUSTER_ONLY;
         h->fgc.cl_umax = forced ? cap : std::min(cap, by_bytes);
         h->fgc.cl_only = c.algo == HTLR_ALGO_CLUSTER_ONLY ? 1 : 0;

@@ -55,7 +55,7 @@ enum { HTLR_RNG_DEVICE = 0, HTLR_RNG_INJECT = 1 };
  *            distributed shared memory and synchronises with hardware cluster barriers: lowest latency per
  *            leapfrog step, for restricted sets of a few hundred columns (falls back to FUSED by itself when
  *            the set is too large). AUTO launches both; the device picks one per iteration from the size of the
- *            restricted set (cluster up to ~3 MB of X[:, iup]).
+ *            restricted set (cluster up to ~1.5 MB of X[:, iup]).
  * Ahead of both, AUTO and CLUSTER_ONLY launch a single-block kernel that runs the trajectory
  * entirely inside one SM (two __syncthreads per leapfrog step) whenever X[:, iup] fits in its shared memory
  * and it is the faster choice (measured: n <= 256 and u * n <= 6000, e.g. the first iterations of config A);
