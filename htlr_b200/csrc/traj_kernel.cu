@@ -251,9 +251,9 @@ __global__ void __launch_bounds__(kFT, 1) k_traj(Geom g, Bufs b, FusedGeom fg, i
   }
   // ---- this group's tile stream: the block's columns are cut into tiles of TC; the group takes tiles
   // grp, grp + NG, ...; the sequence repeats every leapfrog step. Tile i of the stream sits in stage i % SG of
-  // the group's ring; the copies for tile i + SG - 1 are issued when tile i is done. No `empty` barrier is
-  // needed: a stage is refilled only after the group's barriers of the tile that used it (program order for a
-  // one-warp group), and every thread reads its part of a tile into registers before those barriers. If the
+  // the group's ring; the copies for tile i + SG are issued into tile i's own stage as soon as tile i sits in
+  // registers. No `empty` barrier is needed: a stage is refilled only after the group's first barrier of the tile
+  // that used it (program order for a one-warp group), and every thread reads its part of a tile before it. If the
   // group's tiles all fit in its ring they are loaded once and stay resident for the trajectory.
   const int ntiles = (ncols + TC - 1) / TC;
   const int tpg = ntiles > grp ? (ntiles - grp + NG - 1) / NG : 0;     // tiles of this group per step
@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(kFT, 1) k_traj(Geom g, Bufs b, FusedGeom fg, i
     if (++ld_warp == GW) ld_warp = 0;
   };
   {
-    const int pre = (int)(loads_total < SG - 1 ? loads_total : SG - 1);
+    const int pre = (int)(loads_total < SG ? loads_total : SG);
     for (int j = 0; j < pre; ++j) issue_one();
   }
 
@@ -395,6 +395,9 @@ __global__ void __launch_bounds__(kFT, 1) k_traj(Geom g, Bufs b, FusedGeom fg, i
       double* gp = gpart + ((size_t)buf * kCW + grp * GW) * VP;
       if (vwriter) gp[wg * VP + vmine] = vals[0];
       if (GW > 1) named_bar(kBarGroup + grp, GT); else __syncwarp();
+      // every thread of the group has its part of the tile in registers: the stage is free, request the tile SG
+      // ahead into it (SG tiles of the stream are always in flight or landed)
+      if (ld_left > 0) issue_one();
       // ---- one warp of the group: DNlogpost, MoveMomt of step s, UpdateMomtAndDeltas of step s+1;
       // lane <-> (column of the tile, class)
       double* dnb = dnsm + ((size_t)buf * NG + grp) * VP;
@@ -439,8 +442,6 @@ __global__ void __launch_bounds__(kFT, 1) k_traj(Geom g, Bufs b, FusedGeom fg, i
           }
         }
       }
-      // the stage this tile used is free again: request the tile SG-1 ahead into the stage released one tile ago
-      if (ld_left > 0) issue_one();
       if (++stage == SG) { stage = 0; fph ^= 1; }
       if (++pw == GW) pw = 0;
     }
