@@ -12,7 +12,7 @@ python tools/prof_run.py --workload C_default --iters 2 --warm 150 > gpurun_out/
 ncu --metrics gpu__time_duration.sum --clock-control none -s 1360 -c 40 --csv --log-file gpurun_out/launches_restricted.csv \
     python tools/prof_run.py --workload C_default --iters 2 --warm 150 > gpurun_out/ncu_restricted.log 2>&1
 python tools/prof_run.py --workload C_full --iters 2 > gpurun_out/plain_full2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:k_traj -s 1 -c 1 -f -o gpurun_out/prof_traj_v8 \
+ncu --set full --clock-control none --import-source on -k regex:k_traj -s 1 -c 1 -f -o gpurun_out/prof_traj_v9 \
     python tools/prof_run.py --workload C_full --iters 2 > gpurun_out/ncu_full_set.log 2>&1
 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-secondary > gpurun_out/plain_bench.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_bench.csv \
