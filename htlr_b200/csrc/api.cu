@@ -2,7 +2,8 @@
 // sequence (eager or one captured CUDA graph per trajectory length), result fetch, parity hooks and
 // the NCCL plumbing for row-sharded X. No compute happens on the host and there is no CPU fallback.
 #include <cuda_runtime.h>
-#include <nccl.h>
+#include <dlfcn.h>
+#include <nccl.h>   // types and enums only: the library itself is bound at run time (see NcclApi below)
 
 #include <algorithm>
 #include <cmath>
@@ -38,11 +39,49 @@ struct CudaFail {
   do {                                                                                             \
     ncclResult_t r_ = (call);                                                                      \
     if (r_ != ncclSuccess)                                                                         \
-      throw CudaFail{HTLR_E_NCCL, std::string(#call) + ": " + ncclGetErrorString(r_)};             \
+      throw CudaFail{HTLR_E_NCCL, std::string(#call) + ": " + nccl_api().GetErrorString(r_)};             \
   } while (0)
 #define FAIL(code, text) throw CudaFail{code, text}
 
 int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+// NCCL is bound with dlopen on first use instead of being a link-time dependency: only the row-sharded path
+// needs it, and a process that also hosts another NCCL user (a PyTorch that bundles its own, newer libnccl.so.2)
+// must end up with ONE copy of the library, whichever was loaded first, instead of a version clash at load time.
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  std::string error;
+  bool ok = false;
+};
+NcclApi& nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (tried) return api;
+  tried = true;
+  void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) {
+    api.error = std::string("cannot load libnccl.so.2: ") + dlerror();
+    return api;
+  }
+  api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(lib, "ncclGetUniqueId"));
+  api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(lib, "ncclCommInitRank"));
+  api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(lib, "ncclCommDestroy"));
+  api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(lib, "ncclAllReduce"));
+  api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
+  api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.GetErrorString;
+  if (!api.ok) api.error = "libnccl.so.2 lacks an expected symbol";
+  return api;
+}
+NcclApi& nccl_need() {
+  NcclApi& a = nccl_api();
+  if (!a.ok) throw CudaFail{HTLR_E_NCCL, a.error};
+  return a;
+}
 
 struct EventPair {
   cudaEvent_t a, b;
@@ -179,7 +218,7 @@ int enqueue_step(htlr_handle* h, int L, bool until_energy_only = false) {
     if (h->sharded) {
       launch_gsum(g, b, d_u, b.g, st);
       ++nk;
-      NC(ncclAllReduce(b.g, b.g, (size_t)g.nvar * g.K + 1, ncclDouble, ncclSum, h->comm, st));
+      NC(nccl_need().AllReduce(b.g, b.g, (size_t)g.nvar * g.K + 1, ncclDouble, ncclSum, h->comm, st));
     }
     launch_post(g, b, s, L, h->sharded ? 1 : 0, st);
     ++nk;
@@ -511,13 +550,13 @@ void do_create(const htlr_cfg* cfg, const double* X, int64_t ldx, const double* 
 
   // ---- Fit::Fit tail + Fit::Initialize (gibbs.cpp:15, 519-530)
   launch_colsumsq(g, b.X, d_ddn, h->st);
-  if (h->sharded) NC(ncclAllReduce(d_ddn, d_ddn, nvar, ncclDouble, ncclSum, h->comm, h->st));
+  if (h->sharded) NC(nccl_need().AllReduce(d_ddn, d_ddn, nvar, ncclDouble, ncclSum, h->comm, h->st));
   launch_select(g, b, h->st);
   int* d_u = h->ctl_int(offsetof(Ctl, u));
   launch_lv_sweep(g, b, 2, b.iup, d_u, b.deltas, h->st);
   double* d_ll = h->ctl_dbl(offsetof(Ctl, loglike));
   launch_softmax(g, b, 2, d_u, b.lv, b.R, nullptr, d_ll, h->st);
-  if (h->sharded) NC(ncclAllReduce(d_ll, d_ll, 1, ncclDouble, ncclSum, h->comm, h->st));
+  if (h->sharded) NC(nccl_need().AllReduce(d_ll, d_ll, 1, ncclDouble, ncclSum, h->comm, h->st));
   launch_vardeltas_all(g, b, h->st);
   h->launches += 5;
   CU(cudaMemcpyAsync(b.mcdeltas, b.deltas, (size_t)nvar * K * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
@@ -1043,7 +1082,7 @@ int htlr_cuda_nccl_unique_id(void* id128) {
   return guarded(nullptr, [&] {
     static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
     ncclUniqueId id;
-    NC(ncclGetUniqueId(&id));
+    NC(nccl_need().GetUniqueId(&id));
     std::memcpy(id128, &id, sizeof(id));
   });
 }
@@ -1054,13 +1093,13 @@ int htlr_cuda_nccl_init(const void* id128, int32_t rank, int32_t world, int32_t 
     ncclUniqueId id;
     std::memcpy(&id, id128, sizeof(id));
     ncclComm_t c;
-    NC(ncclCommInitRank(&c, world, id, rank));
+    NC(nccl_need().CommInitRank(&c, world, id, rank));
     *comm = c;
   });
 }
 
 void htlr_cuda_nccl_destroy(void* comm) {
-  if (comm) ncclCommDestroy(static_cast<ncclComm_t>(comm));
+  if (comm && nccl_api().ok) nccl_api().CommDestroy(static_cast<ncclComm_t>(comm));
 }
 
 }  // extern "C"

@@ -140,3 +140,67 @@ def test_run_past_the_end_is_refused():
     with pytest.raises(htlr_b200.HtlrCudaError, match="past the configured number"):
         s.run(1)
     s.close()
+
+
+def test_single_call_entry_point_with_tick_callback():
+    """htlr_cuda_fit (the whole of htlr_fit_helper in one C call): same chain as create/run/fetch, the tick callback
+    sees every chunk, and a non-zero return aborts with HTLR_E_STATE."""
+    import ctypes
+    import htlr_b200
+    from htlr_b200 import _lib
+    args = problem(70, 40, 3, seed=6, iters_rmc=300, iters_h=20, leap_L=4, leap_L_h=2)
+    ref = htlr_b200.htlr_fit_helper(**args, seed=9)
+    L = _lib.lib()
+    s = htlr_b200.Sampler(**dict(args, iters_rmc=1, iters_h=0), seed=9)   # only to borrow a filled htlr_cfg
+    cfg = s.cfg
+    s.close()
+    cfg.iters_rmc, cfg.iters_h = args["iters_rmc"], args["iters_h"]
+    nvar, K, H = 41, 2, 301
+    X = np.asfortranarray(args["X"]); ym = np.asfortranarray(args["ymat"]); yb = np.ascontiguousarray(args["ybase"], dtype=np.int64)
+    d0 = np.asfortranarray(args["deltas"]); s0 = np.ascontiguousarray(args["sigmasbt"])
+    out = {k: np.zeros(sh, order="F") for k, sh in (("mcdeltas", (nvar, K, H)), ("mcsigmasbt", (nvar, H)),
+                                                     ("mcvardeltas", (nvar, H)), ("mclogw", H), ("mcloglike", H),
+                                                     ("mcuvar", H), ("mchmcrej", H), ("ddn", nvar))}
+    seen = []
+
+    def tick(user, done, stats, n_chunk):
+        seen.append((done, n_chunk, stats[n_chunk - 1].uvar))
+        return 0
+    cb = _lib.TICK_FN(tick)
+    err = ctypes.create_string_buffer(256)
+    p = lambda a, t=_lib.c_dp: a.ctypes.data_as(t)
+    rc = L.htlr_cuda_fit(ctypes.byref(cfg), p(X), 70, p(ym), p(yb, _lib.c_lp), p(d0), p(s0), None, cb, None,
+                         p(out["mcdeltas"]), p(out["mcsigmasbt"]), p(out["mcvardeltas"]), p(out["mclogw"]),
+                         p(out["mcloglike"]), p(out["mcuvar"]), p(out["mchmcrej"]), p(out["ddn"]), err, 256)
+    assert rc == 0, err.value
+    assert [d for d, _, _ in seen] == [256, 320] and [c for _, c, _ in seen] == [256, 64]   # chunks of 256 (gibbs.cpp:124)
+    assert np.array_equal(out["mcdeltas"], ref["mcdeltas"]) and np.array_equal(out["mcuvar"], ref["mcuvar"].ravel())
+    cb2 = _lib.TICK_FN(lambda user, done, stats, n_chunk: 1)
+    rc = L.htlr_cuda_fit(ctypes.byref(cfg), p(X), 70, p(ym), p(yb, _lib.c_lp), p(d0), p(s0), None, cb2, None,
+                         p(out["mcdeltas"]), p(out["mcsigmasbt"]), p(out["mcvardeltas"]), p(out["mclogw"]),
+                         p(out["mcloglike"]), p(out["mcuvar"]), p(out["mchmcrej"]), p(out["ddn"]), err, 256)
+    assert rc == 5 and b"interrupted" in err.value
+
+
+def test_device_resident_inputs_give_the_same_chain():
+    """htlr_cfg.x_on_device: X / ymat / ybase already in device memory (tall data generated on the GPU)."""
+    import torch
+    import htlr_b200
+    args = problem(130, 60, 3, seed=8, iters_rmc=6, iters_h=3)
+    host = htlr_b200.Sampler(**args, seed=4)
+    host.run(9)
+    a = host.fetch()
+    host.close()
+    n, nvar, K = 130, 61, 2
+    ld = 144
+    Xt = torch.zeros(nvar, ld, dtype=torch.float64, device="cuda")
+    Xt[:, :n] = torch.from_numpy(np.ascontiguousarray(args["X"].T)).cuda()
+    ym = torch.from_numpy(np.ascontiguousarray(np.asarray(args["ymat"]).T)).cuda().contiguous()
+    yb = torch.from_numpy(np.ascontiguousarray(args["ybase"], dtype=np.int64)).cuda()
+    dev = htlr_b200.Sampler(**dict(args, X=None, ymat=None, ybase=None), seed=4,
+                            device_ptrs=(Xt.data_ptr(), ld, ym.data_ptr(), yb.data_ptr()))
+    dev.run(9)
+    b = dev.fetch()
+    dev.close()
+    for k in ("mcdeltas", "mcsigmasbt", "mcloglike", "mcuvar", "mchmcrej"):
+        assert np.array_equal(a[k], b[k]), k
