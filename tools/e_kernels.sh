@@ -1,5 +1,5 @@
 #!/bin/bash
-python bench.py --workload E --n-total 25000 --steps 2 --warmup 3 > gpurun_out/plain_E25k.log 2>&1 && ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum --clock-control none -s 400 -c 16 --csv --log-file gpurun_out/launches_E25k.csv python bench.py --workload E --n-total 25000 --steps 2 --warmup 3 > gpurun_out/ncu_E25k.log 2>&1
+python bench.py --workload E --n-total ${NTOT:-25000} --steps 2 --warmup 3 > gpurun_out/plain_E25k.log 2>&1 && ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum --clock-control none -s 400 -c 16 --csv --log-file gpurun_out/launches_E25k.csv python bench.py --workload E --n-total ${NTOT:-25000} --steps 2 --warmup 3 > gpurun_out/ncu_E25k.log 2>&1
 python - <<'PY'
 import csv
 rows=[r for r in csv.reader(open("gpurun_out/launches_E25k.csv")) if len(r)>10 and r[0].isdigit()]
