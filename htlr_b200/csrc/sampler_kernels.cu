@@ -289,8 +289,16 @@ __global__ void __launch_bounds__(256) k_softmax(Geom g, Bufs b, int what, const
 #pragma unroll
     for (int k = 0; k < KM; ++k) {
       if (k < K) {
+        // slots summed in order, 8 loads in flight at a time (one L2 round trip per 8 slots, not per slot)
         double sacc = 0;
-        for (int s = 0; s < cs.slots; ++s) sacc += b.lvpart[((int64_t)s * K + k) * g.n_s + i];
+        for (int s0 = 0; s0 < cs.slots; s0 += 8) {
+          double pv[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            pv[q] = (s0 + q < cs.slots) ? __ldcg(&b.lvpart[((int64_t)(s0 + q) * K + k) * g.n_s + i]) : 0.0;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) sacc += pv[q];
+        }
         const int64_t e = (int64_t)k * g.n_s + i;
         if (what == 0) {
           const double cur = b.lv[e];
