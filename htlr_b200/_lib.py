@@ -51,7 +51,8 @@ class HtlrProfile(ctypes.Structure):
                 ("sweep_launches", ctypes.c_int64), ("total_ms", ctypes.c_double),
                 ("kernel_launches", ctypes.c_int64), ("sigma_ms", ctypes.c_double),
                 ("fused_sweep_ms", ctypes.c_double), ("fused_barrier_ms", ctypes.c_double),
-                ("fused_rowphase_ms", ctypes.c_double), ("small_kernel_trajectories", ctypes.c_double)]
+                ("fused_rowphase_ms", ctypes.c_double), ("small_kernel_trajectories", ctypes.c_double),
+                ("timeline_us", ctypes.c_double * 12)]
 
 
 TICK_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(HtlrIterStats),
@@ -60,6 +61,7 @@ TICK_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int32, ctypes
 # every symbol include/htlr_cuda.h declares
 EXPORTS = [
     "htlr_cuda_create", "htlr_cuda_destroy", "htlr_cuda_run", "htlr_cuda_fetch", "htlr_cuda_hist_len",
+    "htlr_cuda_collect", "htlr_cuda_release_cache",
     "htlr_cuda_fit", "htlr_cuda_summary", "htlr_cuda_predict", "htlr_cuda_std", "htlr_cuda_eval", "htlr_cuda_trajectory", "htlr_cuda_get_state", "htlr_cuda_ars",
     "htlr_cuda_rng_dump", "htlr_cuda_stream", "htlr_cuda_profile_enable", "htlr_cuda_profile_get",
     "htlr_cuda_launch_count", "htlr_cuda_sync", "htlr_cuda_run_async", "htlr_cuda_nccl_unique_id",
@@ -93,6 +95,8 @@ def lib():
     L.htlr_cuda_launch_count.argtypes = [ctypes.c_void_p]
     L.htlr_cuda_destroy.argtypes = [ctypes.c_void_p]
     L.htlr_cuda_destroy.restype = None
+    L.htlr_cuda_release_cache.restype = None
+    L.htlr_cuda_release_cache.argtypes = []
     L.htlr_cuda_hist_len.argtypes = [ctypes.c_void_p]
     L.htlr_cuda_create.argtypes = [ctypes.POINTER(HtlrCfg), c_dp, ctypes.c_int64, c_dp, c_lp, c_dp, c_dp,
                                    ctypes.POINTER(ctypes.c_void_p)]
@@ -101,6 +105,8 @@ def lib():
     L.htlr_cuda_run_async.argtypes = [ctypes.c_void_p, ctypes.c_int32]
     L.htlr_cuda_sync.argtypes = [ctypes.c_void_p]
     L.htlr_cuda_fetch.argtypes = [ctypes.c_void_p] + [c_dp] * 8
+    L.htlr_cuda_collect.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(HtlrIterStats)] + \
+                                   [c_dp] * 7
     L.htlr_cuda_summary.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_double,
                                     c_dp, c_dp, c_ip]
     L.htlr_cuda_predict.argtypes = [ctypes.c_void_p, c_dp, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,

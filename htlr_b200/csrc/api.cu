@@ -9,8 +9,11 @@
 #include <cmath>
 #include <cstddef>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -83,6 +86,61 @@ NcclApi& nccl_need() {
   return a;
 }
 
+// Device chunks of destroyed handles, kept for the next create on the same device: a fit per CV fold or per chain
+// then pays for cudaMalloc / cudaFree of its arena once per process, not once per fit (a cudaFree of a few hundred
+// megabytes was seen to take > 100 ms now and then). Bounded (HTLR_CACHE_MB, default 4096; 0 disables);
+// htlr_cuda_release_cache() empties it.
+struct ChunkCache {
+  struct Item { int device; void* p; size_t size; };
+  std::mutex mu;
+  std::vector<Item> items;
+  size_t bytes = 0;
+  static size_t limit() {
+    static const size_t lim = [] {
+      const char* e = std::getenv("HTLR_CACHE_MB");
+      return (size_t)(e ? std::max(0L, std::atol(e)) : 4096L) << 20;
+    }();
+    return lim;
+  }
+  void* take(int device, size_t want, size_t* got) {
+    std::lock_guard<std::mutex> lk(mu);
+    int best = -1;
+    for (int i = 0; i < (int)items.size(); ++i)
+      if (items[i].device == device && items[i].size >= want && items[i].size <= 2 * want + ((size_t)8 << 20) &&
+          (best < 0 || items[i].size < items[best].size))
+        best = i;
+    if (best < 0) return nullptr;
+    void* p = items[best].p;
+    *got = items[best].size;
+    bytes -= items[best].size;
+    items.erase(items.begin() + best);
+    return p;
+  }
+  bool give(int device, void* p, size_t size) {
+    std::lock_guard<std::mutex> lk(mu);
+    if (bytes + size > limit()) return false;
+    items.push_back({device, p, size});
+    bytes += size;
+    return true;
+  }
+  void clear() {
+    std::lock_guard<std::mutex> lk(mu);
+    for (auto& it : items) {
+      int cur = 0;
+      cudaGetDevice(&cur);
+      cudaSetDevice(it.device);
+      cudaFree(it.p);
+      cudaSetDevice(cur);
+    }
+    items.clear();
+    bytes = 0;
+  }
+};
+ChunkCache& chunk_cache() {
+  static ChunkCache c;
+  return c;
+}
+
 struct EventPair {
   cudaEvent_t a, b;
   int kind;  // 0 sweep, 1 step total, 2 sigma
@@ -109,6 +167,7 @@ struct htlr_handle {
   bool use_small = false;   // launch the single-block kernel ahead of both
   int smem_optin = 0;
   unsigned long long small_base = 0;
+  unsigned long long tl_base[12] = {};
   bool profiling = false;
   std::vector<EventPair> ev_pool;
   size_t ev_used = 0;
@@ -126,6 +185,12 @@ struct htlr_handle {
   double *inj[4] = {nullptr, nullptr, nullptr, nullptr};
   int64_t inj_cap[4] = {0, 0, 0, 0};
   unsigned long long cols_base = 0;  // Ctl::cols_swept at the last profile reset
+  // pipelined download (htlr_cuda_collect): an event after every enqueue call, a copy stream of its own
+  struct Mark { int iters; cudaEvent_t ev; };
+  std::deque<Mark> marks;
+  std::vector<cudaEvent_t> mark_free;
+  cudaStream_t st_copy = nullptr;
+  int slices_collected = 0;
   unsigned long long ph_base[4] = {0, 0, 0, 0};
 
   // Device memory comes from a few large chunks (one cudaMalloc / cudaFree each): creating and destroying a
@@ -134,10 +199,11 @@ struct htlr_handle {
   struct Chunk { char* base; size_t size, used; };
   std::vector<Chunk> chunks;
   void arena_reserve(size_t bytes) {
-    void* p = nullptr;
-    CU(cudaMalloc(&p, bytes));
+    size_t got = bytes;
+    void* p = chunk_cache().take(cfg.device, bytes, &got);
+    if (!p) CU(cudaMalloc(&p, bytes));
     allocs.push_back(p);
-    chunks.push_back(Chunk{static_cast<char*>(p), bytes, 0});
+    chunks.push_back(Chunk{static_cast<char*>(p), got, 0});
   }
   template <class T>
   T* dalloc(size_t count, bool zero = true) {
@@ -286,15 +352,18 @@ int enqueue_step(htlr_handle* h, int L, bool until_energy_only = false) {
   return nk;
 }
 
-cudaGraphExec_t get_graph(htlr_handle* h, int L) {
-  const int key = 2 * L + (h->use_cluster ? 1 : 0);
+// One graph = `reps` consecutive thin-steps with the same trajectory length (reps > 1 saves the launch gap between
+// consecutive graphs: one cudaGraphLaunch per unit of iterations).
+constexpr int kGraphReps = 8;
+cudaGraphExec_t get_graph(htlr_handle* h, int L, int reps = 1) {
+  const int key = (2 * L + (h->use_cluster ? 1 : 0)) * 16 + reps;
   auto it = h->graphs.find(key);
   if (it != h->graphs.end()) return it->second;
   cudaGraph_t graph;
   CU(cudaStreamBeginCapture(h->st, cudaStreamCaptureModeThreadLocal));
   int nk = 0;
   try {
-    nk = enqueue_step(h, L);
+    for (int r = 0; r < reps; ++r) nk = enqueue_step(h, L);
   } catch (...) {
     cudaGraph_t junk = nullptr;
     cudaStreamEndCapture(h->st, &junk);
@@ -539,6 +608,10 @@ void do_create(const htlr_cfg* cfg, const double* X, int64_t ldx, const double* 
   ctl.iters_h = c.iters_h; ctl.iters_rmc = c.iters_rmc; ctl.thin = c.thin;
   ctl.keep_warmup_hist = c.keep_warmup_hist ? 1 : 0;
   ctl.ptype = c.ptype; ctl.rng_mode = c.rng_mode;
+  {
+    const char* e = getenv("HTLR_TIMELINE");
+    ctl.timeline = e && atoi(e) > 0;
+  }
   ctl.alpha = c.alpha; ctl.s = c.s; ctl.eta = c.eta; ctl.leap_step = c.leap_step;
   ctl.sgmsq_cut = c.hmc_sgmcut > 0 ? c.hmc_sgmcut * c.hmc_sgmcut : c.hmc_sgmcut;  // gibbs.cpp:14
   ctl.seed = c.seed;
@@ -639,11 +712,17 @@ void htlr_cuda_destroy(htlr_handle* h) {
   if (h->st) cudaStreamSynchronize(h->st);
   drop_graphs(h);
   for (auto& p : h->ev_pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
-  for (void* p : h->allocs) cudaFree(p);
+  for (auto& m : h->marks) cudaEventDestroy(m.ev);
+  for (cudaEvent_t e : h->mark_free) cudaEventDestroy(e);
+  if (h->st_copy) { cudaStreamSynchronize(h->st_copy); cudaStreamDestroy(h->st_copy); }
+  for (auto& c : h->chunks)
+    if (!chunk_cache().give(h->cfg.device, c.base, c.size)) cudaFree(c.base);
   for (int q = 0; q < 4; ++q) if (h->inj[q]) cudaFree(h->inj[q]);
   if (h->st) cudaStreamDestroy(h->st);
   delete h;
 }
+
+void htlr_cuda_release_cache(void) { chunk_cache().clear(); }
 
 int32_t htlr_cuda_hist_len(const htlr_handle* h) {
   return h->cfg.iters_rmc + 1 + (h->cfg.keep_warmup_hist ? h->cfg.iters_h : 0);
@@ -655,8 +734,18 @@ static void enqueue_iters(htlr_handle* h, int32_t n_iters) {
     FAIL(HTLR_E_STATE, "run past the configured number of iterations");
   CU(cudaSetDevice(c.device));
   const bool graph = c.use_graph && !h->profiling;
+  static const bool multi = [] { const char* e = std::getenv("HTLR_GRAPH_REPS"); return !e || std::atoi(e) != 1; }();
   for (int it = 0; it < n_iters; ++it) {
     const int L = pick_L(c, h->iters_done);
+    if (graph && multi && c.thin == 1 && it + kGraphReps <= n_iters &&
+        pick_L(c, h->iters_done + kGraphReps - 1) == L) {
+      // kGraphReps iterations of the same phase in one launch (pick_L is monotone in the iteration index)
+      CU(cudaGraphLaunch(get_graph(h, L, kGraphReps), h->st));
+      h->launches += (int64_t)kGraphReps * kernels_per_step(h, L);
+      h->iters_done += kGraphReps;
+      it += kGraphReps - 1;
+      continue;
+    }
     for (int t = 0; t < c.thin; ++t) {
       if (graph) {
         cudaGraphExec_t ge = get_graph(h, L);
@@ -668,6 +757,18 @@ static void enqueue_iters(htlr_handle* h, int32_t n_iters) {
       }
     }
     h->iters_done += 1;
+  }
+  if (n_iters > 0) {
+    // completion mark of this call (htlr_cuda_collect waits on it instead of on the whole stream)
+    cudaEvent_t ev;
+    if (!h->mark_free.empty()) { ev = h->mark_free.back(); h->mark_free.pop_back(); }
+    else CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CU(cudaEventRecord(ev, h->st));
+    h->marks.push_back({h->iters_done, ev});
+    while (h->marks.size() > 256) {   // nobody is collecting: a later mark covers the earlier ones
+      h->mark_free.push_back(h->marks.front().ev);
+      h->marks.pop_front();
+    }
   }
 }
 
@@ -724,6 +825,55 @@ int htlr_cuda_fetch(htlr_handle* h, double* mcdeltas, double* mcsigmasbt, double
     get(mcuvar, h->b.mcuvar, H);
     get(mchmcrej, h->b.mchmcrej, H);
     get(ddnloglike, h->b.ddn, nvar);
+  });
+}
+
+int htlr_cuda_collect(htlr_handle* h, int32_t upto_iters, int32_t stats_from, htlr_iter_stats* stats, double* mcdeltas,
+                      double* mcsigmasbt, double* mcvardeltas, double* mclogw, double* mcloglike, double* mcuvar,
+                      double* mchmcrej) {
+  if (!h) return HTLR_E_ARG;
+  return guarded(h, [&] {
+    const htlr_cfg& c = h->cfg;
+    if (upto_iters < 0 || upto_iters > h->iters_done) FAIL(HTLR_E_STATE, "collect past the enqueued iterations");
+    if (stats && (stats_from < 0 || stats_from > upto_iters)) FAIL(HTLR_E_ARG, "bad stats range");
+    CU(cudaSetDevice(c.device));
+    if (!h->st_copy) CU(cudaStreamCreateWithFlags(&h->st_copy, cudaStreamNonBlocking));
+    // the earliest completion mark that covers `upto_iters`; later work on the compute stream is not waited for
+    bool covered = upto_iters == 0;
+    while (!h->marks.empty() && !covered) {
+      htlr_handle::Mark m = h->marks.front();
+      if (m.iters >= upto_iters) {
+        CU(cudaStreamWaitEvent(h->st_copy, m.ev, 0));
+        covered = true;
+        if (m.iters > upto_iters) break;   // keep it for the next call
+      }
+      h->mark_free.push_back(m.ev);
+      h->marks.pop_front();
+    }
+    if (!covered) CU(cudaStreamSynchronize(h->st));   // marks were recycled: fall back to the whole stream
+    const size_t nvar = h->g.nvar, K = h->g.K;
+    const int avail = 1 + (c.keep_warmup_hist ? upto_iters : std::max(0, upto_iters - c.iters_h));
+    const int s0 = h->slices_collected, ns = avail - s0;
+    auto get = [&](double* dst, const double* src, size_t per_slice) {
+      if (dst && ns > 0)
+        CU(cudaMemcpyAsync(dst + per_slice * s0, src + per_slice * s0, per_slice * ns * sizeof(double),
+                           cudaMemcpyDeviceToHost, h->st_copy));
+    };
+    get(mcdeltas, h->b.mcdeltas, nvar * K);
+    get(mcsigmasbt, h->b.mcsigmasbt, nvar);
+    get(mcvardeltas, h->b.mcvardeltas, nvar);
+    get(mclogw, h->b.mclogw, 1);
+    get(mcloglike, h->b.mcloglike, 1);
+    get(mcuvar, h->b.mcuvar, 1);
+    get(mchmcrej, h->b.mchmcrej, 1);
+    if (stats && upto_iters > stats_from) {
+      static_assert(sizeof(htlr_iter_stats) == sizeof(Red4), "stats layout");
+      CU(cudaMemcpyAsync(stats, h->b.stats + stats_from, sizeof(Red4) * (upto_iters - stats_from),
+                         cudaMemcpyDeviceToHost, h->st_copy));
+    }
+    CU(cudaStreamSynchronize(h->st_copy));
+    if (ns > 0) h->slices_collected = avail;
+    check_device_error(h);
   });
 }
 
@@ -1029,12 +1179,14 @@ int htlr_cuda_profile_get(htlr_handle* h, htlr_profile* out, int32_t reset) {
     h->prof.fused_barrier_ms = (double)(c.ph_cycles[1] - h->ph_base[1] + c.ph_cycles[3] - h->ph_base[3]) / per_ms;
     h->prof.fused_rowphase_ms = (double)(c.ph_cycles[2] - h->ph_base[2]) / per_ms;
     h->prof.small_kernel_trajectories = (double)(c.small_runs - h->small_base);
+    for (int q = 0; q < 12; ++q) h->prof.timeline_us[q] = (double)(c.tl_acc[q] - h->tl_base[q]) * 1e-3;
     *out = h->prof;
     if (reset) {
       h->prof = htlr_profile{};
       h->cols_base = c.cols_swept;
       for (int q = 0; q < 4; ++q) h->ph_base[q] = c.ph_cycles[q];
       h->small_base = c.small_runs;
+      for (int q = 0; q < 12; ++q) h->tl_base[q] = c.tl_acc[q];
     }
   });
 }
@@ -1062,15 +1214,28 @@ int htlr_cuda_fit(const htlr_cfg* cfg, const double* X, int64_t ldx, const doubl
     if (rc) return fail(rc, htlr_cuda_last_error(h));
     if (tick && tick(user, total, st.data(), total)) return fail(HTLR_E_STATE, "interrupted");
   } else {
-    std::vector<htlr_iter_stats> st(256);
-    for (int done = 0; done < total;) {
-      // the reference polls for interrupts when i_mc % 256 == 0 (gibbs.cpp:124)
-      const int chunk = std::min(256, total - done);
-      rc = htlr_cuda_run(h, chunk, nullptr, st.data());
+    // Pipelined: kUnit iterations per enqueue call, up to kDepth iterations in flight; the trace slices and stats of
+    // a unit are copied out while the following units run, so only the last unit's download is exposed. The tick
+    // (progress line + interrupt poll; the reference polls every 256 iterations, gibbs.cpp:124) runs per unit.
+    constexpr int kUnit = 8, kDepth = 64;
+    std::vector<htlr_iter_stats> st(kUnit);
+    int enq = 0, done = 0;
+    while (done < total) {
+      while (enq < total && enq - done < kDepth) {
+        const int nq = std::min(kUnit, total - enq);
+        rc = htlr_cuda_run_async(h, nq);
+        if (rc) return fail(rc, htlr_cuda_last_error(h));
+        enq += nq;
+      }
+      const int upto = std::min(done + kUnit, total);
+      rc = htlr_cuda_collect(h, upto, done, st.data(), mcdeltas, mcsigmasbt, mcvardeltas, mclogw, mcloglike, mcuvar,
+                             mchmcrej);
       if (rc) return fail(rc, htlr_cuda_last_error(h));
-      done += chunk;
-      if (tick && tick(user, done, st.data(), chunk)) return fail(HTLR_E_STATE, "interrupted");
+      const int nd = upto - done;
+      done = upto;
+      if (tick && tick(user, done, st.data(), nd)) return fail(HTLR_E_STATE, "interrupted");
     }
+    mcdeltas = mcsigmasbt = mcvardeltas = mclogw = mcloglike = mcuvar = mchmcrej = nullptr;   // already collected
   }
   rc = htlr_cuda_fetch(h, mcdeltas, mcsigmasbt, mcvardeltas, mclogw, mcloglike, mcuvar, mchmcrej, ddnloglike);
   if (rc) return fail(rc, htlr_cuda_last_error(h));

@@ -50,9 +50,36 @@ struct Ctl {
   // fused trajectory kernel, block 0: SM cycles spent in the column sweep, the two grid barriers and the
   // row phase (partial reduction + softmax), accumulated over launches (htlr_profile.fused_*_ms)
   unsigned long long ph_cycles[4];
+  // per-iteration timeline (HTLR_TIMELINE=1): tl_acc[k] accumulates the %globaltimer nanoseconds between the
+  // start of the previous marked kernel of the iteration and the start of kernel k (0 select, 1 begin,
+  // 2 detach sweep, 3 softmax, 4 single-block trajectory, 5 cluster-mode, 6 grid-mode, 7 energy, 8 tail)
+  int timeline;
+  unsigned long long tl_prev, tl_acc[12];
   // scratch counters for "last block finishes" reductions
   unsigned int ticket[8];
 };
+
+// Start-of-kernel time stamp for the per-iteration timeline; the marked kernels of an iteration run one after
+// the other, so the read-modify-write needs no atomics.
+__device__ __forceinline__ void timeline_mark(Ctl* ctl, int k) {
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && ctl->timeline) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)::"memory");
+    ctl->tl_acc[k] += t - ctl->tl_prev;
+    ctl->tl_prev = t;
+  }
+}
+
+// End-of-kernel stamp, called by the one thread that finishes the kernel's last-block epilogue
+// (9 tail, 10 energy, 11 begin): separates a kernel's own time from the gap to the next kernel's start.
+__device__ __forceinline__ void timeline_mark_end(Ctl* ctl, int k) {
+  if (ctl->timeline) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)::"memory");
+    ctl->tl_acc[k] += t - ctl->tl_prev;
+    ctl->tl_prev = t;
+  }
+}
 
 struct Red4 {
   double a, b, c, d;

@@ -64,6 +64,7 @@ __global__ void k_colsumsq(Geom g, const double* __restrict__ X, double* __restr
 // pass 1 counts, an exclusive scan over the 32 warp totals gives each warp its output offset, pass 2 writes.
 __global__ void __launch_bounds__(1024) k_select(Geom g, Bufs b) {
   Ctl* ctl = b.ctl;
+  timeline_mark(ctl, 0);
   __shared__ int s_w[32];
   __shared__ int s_total;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -119,6 +120,7 @@ __global__ void __launch_bounds__(1024) k_select(Geom g, Bufs b) {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_begin(Geom g, Bufs b) {
   Ctl* ctl = b.ctl;
+  timeline_mark(ctl, 1);
   __shared__ double sm[32];
   const int u = ctl->u, K = g.K, nvar = g.nvar;
   const KeyedRng rng{ctl->seed};
@@ -159,6 +161,7 @@ __global__ void __launch_bounds__(256) k_begin(Geom g, Bufs b) {
       ctl->loglike_old = ctl->loglike;
       ctl->ticket[4] = 0;  // grid-barrier counter of the fused trajectory kernel
       ctl->traj_done = 0;
+      timeline_mark_end(ctl, 11);
     }
   }
 }
@@ -209,6 +212,7 @@ __global__ void __launch_bounds__(256) k_lv_sweep(Geom g, Bufs b, int mode, cons
   double* s_coef = reinterpret_cast<double*>(lv_smem);                    // [kLvChunk][K]
   int64_t* s_off = reinterpret_cast<int64_t*>(s_coef + (size_t)kLvChunk * K);  // [kLvChunk] column offsets (doubles)
   const ColSet cs = resolve_cols(g, b, mode, idx_in, cnt_in, coef_global);
+  if (mode == 0) timeline_mark(b.ctl, 2);
   const int s = blockIdx.x;
   if (s == 0 && blockIdx.y == 0 && threadIdx.x == 0) b.ctl->cols_swept += (unsigned long long)cs.cnt;
   if (s >= cs.slots) return;
@@ -281,6 +285,7 @@ __global__ void __launch_bounds__(256) k_softmax(Geom g, Bufs b, int what, const
   const int K = KT > 0 ? KT : g.K;
   Ctl* ctl = b.ctl;
   __shared__ double sm[32];
+  if (what == 0) timeline_mark(ctl, 3);
   const ColSet cs = resolve_cols(g, b, what == 0 ? 0 : (what == 1 ? 1 : 2), nullptr, cnt_in, nullptr);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   double ll = 0;
@@ -471,6 +476,7 @@ __global__ void __launch_bounds__(256) k_post(Geom g, Bufs b, int s, int L, int 
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_energy(Geom g, Bufs b, int g_has_loglike) {
   Ctl* ctl = b.ctl;
+  timeline_mark(ctl, 7);
   __shared__ double sm[32];
   const int u = ctl->u, K = g.K;
   const double Cd = (double)ctl->C;
@@ -517,6 +523,7 @@ __global__ void __launch_bounds__(256) k_energy(Geom g, Bufs b, int g_has_loglik
       const bool reject = (log(uu) > (ne - ctl->nenergy_old)) || (F > 0);
       ctl->accept = reject ? 0 : 1;
       if (reject) ctl->rej_acc += 1;
+      timeline_mark_end(ctl, 10);
     }
   }
 }

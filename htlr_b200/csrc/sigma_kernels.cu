@@ -42,6 +42,7 @@ __global__ void __launch_bounds__(256) k_sigma_t(Geom g, Bufs b) {
 // drawn and its trace entries are written.
 __global__ void __launch_bounds__(256) k_tail_t(Geom g, Bufs b) {
   Ctl* ctl = b.ctl;
+  timeline_mark(ctl, 8);
   const int nvar = g.nvar, K = g.K, p = ctl->p;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
   const bool accept = ctl->accept != 0;
@@ -114,6 +115,7 @@ __global__ void __launch_bounds__(256) k_tail_t(Geom g, Bufs b) {
       } else {
         ctl->i_thin += 1;
       }
+      timeline_mark_end(ctl, 9);
     }
   }
 }

@@ -33,6 +33,7 @@ __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cv
 template <int KT>
 __global__ void __launch_bounds__(kST, 1) k_traj_small(Geom g, Bufs b, int L, int smem_doubles, int u_max) {
   Ctl* ctl = b.ctl;
+  timeline_mark(ctl, 4);
   if (ctl->traj_done) return;
   const int u = ctl->u;
   const int n = g.n, n_s = g.n_s, npairs = (n + 1) >> 1, n_e = 2 * npairs;

@@ -151,6 +151,7 @@ __global__ void __launch_bounds__(kFT, 1) k_traj(Geom g, Bufs b, FusedGeom fg, i
   constexpr int V = TC * KT;             // (column, class) gradient values per tile
   constexpr int VP = V <= 4 ? 4 : 8;     // padded to a power of two for the transposing reduction
   Ctl* ctl = b.ctl;
+  timeline_mark(ctl, CL ? 5 : 6);
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int n = g.n, n_s = g.n_s, npairs = (n + 1) >> 1, n_e = 2 * npairs;
   const int SG = fg.NS;                  // ring stages (tiles) per group

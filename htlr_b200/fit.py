@@ -143,16 +143,42 @@ class Sampler:
     def sync(self):
         self._check(_lib.lib().htlr_cuda_sync(self.h))
 
-    def fetch(self):
-        """Fit::OutputR (gibbs.cpp:128-152)."""
+    _TRACE = ("mcdeltas", "mcsigmasbt", "mcvardeltas", "mclogw", "mcloglike", "mcuvar", "mchmcrej")
+
+    def trace_arrays(self):
+        """Host arrays with the shapes of Fit::OutputR's trace members (gibbs.cpp:128-152)."""
         H, nvar, K = self.hist_len, self.nvar, self.K
-        o = {"mcdeltas": np.zeros((nvar, K, H), order="F"), "mcsigmasbt": np.zeros((nvar, H), order="F"),
-             "mcvardeltas": np.zeros((nvar, H), order="F"), "mclogw": np.zeros((H, 1)),
-             "mcloglike": np.zeros((H, 1)), "mcuvar": np.zeros((H, 1)), "mchmcrej": np.zeros((H, 1))}
+        return {"mcdeltas": np.zeros((nvar, K, H), order="F"), "mcsigmasbt": np.zeros((nvar, H), order="F"),
+                "mcvardeltas": np.zeros((nvar, H), order="F"), "mclogw": np.zeros((H, 1)),
+                "mcloglike": np.zeros((H, 1)), "mcuvar": np.zeros((H, 1)), "mchmcrej": np.zeros((H, 1))}
+
+    def collect(self, upto_iters, into, stats_from=None):
+        """Pipelined download (htlr_cuda_collect): waits for the first `upto_iters` iterations only, copies the trace
+        slices completed since the last collect into `into` (from trace_arrays(); the same dict every call) and
+        returns the per-iteration scalars of iterations [stats_from, upto_iters)."""
+        ns = 0 if stats_from is None else upto_iters - stats_from
+        st = (HtlrIterStats * max(ns, 1))()
+        self._check(_lib.lib().htlr_cuda_collect(self.h, upto_iters, 0 if stats_from is None else stats_from,
+                                                 st if ns > 0 else None, *[_ptr(into[k]) for k in self._TRACE]))
+        return {"loglike": np.array([st[i].loglike for i in range(ns)]),
+                "logw": np.array([st[i].logw for i in range(ns)]),
+                "uvar": np.array([st[i].uvar for i in range(ns)]),
+                "rej": np.array([st[i].rej for i in range(ns)])}
+
+    def fetch(self, collected=None):
+        """Fit::OutputR (gibbs.cpp:128-152). `collected`: trace arrays already filled by collect() up to the last
+        iteration — only the remaining members are downloaded then."""
+        nvar = self.nvar
         ddn = np.zeros((1, nvar))
-        self._check(_lib.lib().htlr_cuda_fetch(self.h, _ptr(o["mcdeltas"]), _ptr(o["mcsigmasbt"]),
-                                               _ptr(o["mcvardeltas"]), _ptr(o["mclogw"]), _ptr(o["mcloglike"]),
-                                               _ptr(o["mcuvar"]), _ptr(o["mchmcrej"]), _ptr(ddn)))
+        if collected is not None:
+            o = collected
+            null = ctypes.cast(None, c_dp)
+            self._check(_lib.lib().htlr_cuda_fetch(self.h, null, null, null, null, null, null, null, _ptr(ddn)))
+        else:
+            o = self.trace_arrays()
+            self._check(_lib.lib().htlr_cuda_fetch(self.h, _ptr(o["mcdeltas"]), _ptr(o["mcsigmasbt"]),
+                                                   _ptr(o["mcvardeltas"]), _ptr(o["mclogw"]), _ptr(o["mcloglike"]),
+                                                   _ptr(o["mcuvar"]), _ptr(o["mchmcrej"]), _ptr(ddn)))
         sg = self.hmc_sgmcut
         out = {"p": self.p, "n": self.n, "K": self.K,
                "mc.param": {"iter.rmc": self.iters_rmc, "iter.warm": self.iters_h, "thin": self.thin,
@@ -231,9 +257,11 @@ class Sampler:
     def profile_get(self, reset=False):
         pr = HtlrProfile()
         self._check(_lib.lib().htlr_cuda_profile_get(self.h, ctypes.byref(pr), int(reset)))
-        return {k: getattr(pr, k) for k in ("sweep_ms", "sweep_bytes", "sweep_launches", "total_ms",
-                                            "kernel_launches", "sigma_ms", "fused_sweep_ms",
-                                            "fused_barrier_ms", "fused_rowphase_ms", "small_kernel_trajectories")}
+        out = {k: getattr(pr, k) for k in ("sweep_ms", "sweep_bytes", "sweep_launches", "total_ms",
+                                           "kernel_launches", "sigma_ms", "fused_sweep_ms",
+                                           "fused_barrier_ms", "fused_rowphase_ms", "small_kernel_trajectories")}
+        out["timeline_us"] = list(pr.timeline_us)
+        return out
 
     @property
     def launch_count(self):
@@ -245,25 +273,41 @@ def htlr_fit_helper(p, K, n, X, ymat, ybase, ptype, alpha, s, eta, iters_rmc, it
                     seed=0, progress=None, **kw):
     """Drop-in for the reference's `htlr_fit_helper` (src/main.cpp:7-25): Fit ctor, StartSampling, OutputR.
 
-    Runs in chunks of 256 iterations like the reference's interrupt poll (gibbs.cpp:124); when
-    `silence == 0` prints the reference's progress line (gibbs.cpp:119-121) per iteration.
+    Pipelined like htlr_cuda_fit: units of 8 iterations, up to 64 in flight, each unit's trace slices downloaded
+    while the following units run; `progress(done, stats)` (the reference polls for interrupts every 256
+    iterations, gibbs.cpp:124) is called per unit; when `silence == 0` the reference's progress line
+    (gibbs.cpp:119-121) is printed per iteration. Injected random streams are positional, so that mode runs in
+    one blocking call.
     """
+    streams = {k: kw.pop(k, None) for k in ("normals", "uniforms", "gammas", "ars_uniforms")}
     smp = Sampler(p, K, n, X, ymat, ybase, ptype, alpha, s, eta, iters_rmc, iters_h, thin, leap_L, leap_L_h,
                   leap_step, hmc_sgmcut, deltas, sigmasbt, keep_warmup_hist, silence, legacy, device=device,
                   seed=seed, **kw)
     try:
-        total, done = iters_h + iters_rmc, 0
+        total, done, enq = iters_h + iters_rmc, 0, 0
+        inject = smp.cfg.rng_mode == RNG_INJECT
+        want_stats = silence == 0 or progress is not None
+        out = None if inject else smp.trace_arrays()
+        unit, depth = 8, 64
         while done < total:
-            chunk = min(256, total - done)
-            st = smp.run(chunk)
+            if inject:
+                upto = total
+                st = smp.run(total, **streams)
+            else:
+                while enq < total and enq - done < depth:
+                    nq = min(unit, total - enq)
+                    smp.run_async(nq)
+                    enq += nq
+                upto = min(done + unit, total)
+                st = smp.collect(upto, out, stats_from=done if want_stats else None)
             if silence == 0:
-                for i in range(chunk):
+                for i in range(upto - done):
                     print("Iter%4d: deviance=%5.3f, logw=%6.2f, nuvar=%3.0f, hmcrej=%4.2f"
                           % (done + i - iters_h, -st["loglike"][i] / n, st["logw"][i], st["uvar"][i], st["rej"][i]))
-            done += chunk
+            done = upto
             if progress is not None and progress(done, st):
                 raise HtlrCudaError(5, "interrupted")
-        return smp.fetch()
+        return smp.fetch(collected=out)
     finally:
         smp.close()
 

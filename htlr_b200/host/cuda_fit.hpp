@@ -90,28 +90,63 @@ class CudaFit {
   CudaFit& operator=(const CudaFit&) = delete;
   ~CudaFit() { htlr_cuda_destroy(h_); }
 
-  // Fit::StartSampling (gibbs.cpp:52-126). Device RNG: chunks of 256 iterations, the reference's
-  // interrupt-poll period (gibbs.cpp:124). Injected variates are positional, so they run as one call.
+  // Fit::StartSampling (gibbs.cpp:52-126). Device RNG: pipelined — units of 8 iterations, up to 64 in flight,
+  // each unit's trace slices copied into the output arrays while the following units run (htlr_cuda_collect);
+  // progress() is called per unit, far inside the reference's interrupt-poll period of 256 iterations
+  // (gibbs.cpp:124). Injected variates are positional, so they run as one blocking call.
   void StartSampling(const Progress& progress = nullptr) {
     const int total = cfg_.iters_h + cfg_.iters_rmc;
-    const int chunk_max = inject_ ? total : 256;
-    std::vector<htlr_iter_stats> st(chunk_max > 0 ? chunk_max : 1);
+    const int unit = inject_ ? total : 8, depth = 64;
+    std::vector<htlr_iter_stats> st(unit > 0 ? unit : 1);
+    if (!inject_) { size_output(); collected_ = true; }
+    int enq = 0;
     for (int done = 0; done < total;) {
-      const int chunk = total - done < chunk_max ? total - done : chunk_max;
-      check(htlr_cuda_run(h_, chunk, inject_, st.data()));
+      const int upto = total - done < unit ? total : done + unit;
+      if (inject_) {
+        check(htlr_cuda_run(h_, total, inject_, st.data()));
+      } else {
+        while (enq < total && enq - done < depth) {
+          const int nq = total - enq < unit ? total - enq : unit;
+          check(htlr_cuda_run_async(h_, nq));
+          enq += nq;
+        }
+        check(htlr_cuda_collect(h_, upto, done, st.data(), out_.mcdeltas.data(), out_.mcsigmasbt.data(),
+                                out_.mcvardeltas.data(), out_.mclogw.data(), out_.mcloglike.data(),
+                                out_.mcuvar.data(), out_.mchmcrej.data()));
+      }
+      const int chunk = upto - done;
       if (cfg_.silence == 0) {
         for (int i = 0; i < chunk; ++i)   // gibbs.cpp:119-121
           std::printf("Iter%4d: deviance=%5.3f, logw=%6.2f, nuvar=%3.0f, hmcrej=%4.2f\n", done + i - cfg_.iters_h,
                       -st[i].loglike / cfg_.n, st[i].logw, st[i].uvar, st[i].rej);
       }
-      done += chunk;
+      done = upto;
       if (progress && progress(done, st.data(), chunk)) throw CudaFitError(HTLR_E_STATE, "interrupted");
     }
   }
 
   // Fit::OutputR (gibbs.cpp:128-152).
   FitOutput Output() {
-    FitOutput o;
+    size_output();
+    FitOutput& o = out_;
+    if (collected_) {   // the trace arrived during StartSampling
+      check(htlr_cuda_fetch(h_, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, o.DDNloglike.data()));
+    } else {
+      check(htlr_cuda_fetch(h_, o.mcdeltas.data(), o.mcsigmasbt.data(), o.mcvardeltas.data(), o.mclogw.data(),
+                            o.mcloglike.data(), o.mcuvar.data(), o.mchmcrej.data(), o.DDNloglike.data()));
+    }
+    FitOutput r = std::move(out_);   // a later call downloads everything again
+    out_ = FitOutput();
+    collected_ = false;
+    return r;
+  }
+
+  htlr_handle* handle() { return h_; }
+
+ private:
+  void size_output() {
+    FitOutput& o = out_;
+    if (o.hist_len) return;
     const size_t nvar = (size_t)cfg_.p + 1, K = (size_t)cfg_.K, H = (size_t)htlr_cuda_hist_len(h_);
     o.p = cfg_.p; o.n = cfg_.n; o.K = cfg_.K;
     o.iter_rmc = cfg_.iters_rmc; o.iter_warm = cfg_.iters_h; o.thin = cfg_.thin;
@@ -123,20 +158,15 @@ class CudaFit {
     o.mcsigmasbt.resize(nvar * H);
     o.mcvardeltas.resize(nvar * H);
     o.mclogw.resize(H); o.mcloglike.resize(H); o.mcuvar.resize(H); o.mchmcrej.resize(H);
-    check(htlr_cuda_fetch(h_, o.mcdeltas.data(), o.mcsigmasbt.data(), o.mcvardeltas.data(), o.mclogw.data(),
-                          o.mcloglike.data(), o.mcuvar.data(), o.mchmcrej.data(), o.DDNloglike.data()));
-    return o;
   }
-
-  htlr_handle* handle() { return h_; }
-
- private:
   void check(int rc) {
     if (rc) throw CudaFitError(rc, htlr_cuda_last_error(h_));
   }
   htlr_cfg cfg_;
   htlr_handle* h_ = nullptr;
   const htlr_inject* inject_;
+  FitOutput out_;
+  bool collected_ = false;
 };
 
 // The reference's free function (main.cpp:7-25), same 22 arguments in the same order.

@@ -120,6 +120,12 @@ typedef struct htlr_profile {
    * waiting at the two grid-wide barriers of each leapfrog step, and in the row phase between them */
   double fused_sweep_ms, fused_barrier_ms, fused_rowphase_ms;
   double small_kernel_trajectories;   /* proposals run by the single-block kernel since create / reset */
+  /* per-iteration timeline, collected only when the handle was created with HTLR_TIMELINE=1 in the environment
+   * (graph replay stays on): microseconds from the start of the previous kernel of the iteration to the start of
+   * kernel k, summed over iterations — 0 select (i.e. the tail of the previous iteration), 1 begin, 2 detach
+   * sweep, 3 softmax, 4 single-block trajectory, 5 cluster-mode trajectory, 6 grid-mode trajectory, 7 energy,
+   * 8 tail */
+  double timeline_us[12];
 } htlr_profile;
 
 /* Replaces `Fit::Fit` + `Fit::Initialize` (gibbs.cpp:4-50, 519-530).
@@ -130,6 +136,9 @@ int htlr_cuda_create(const htlr_cfg* cfg, const double* X, int64_t ldx, const do
                      const int64_t* ybase, const double* deltas0, const double* sigmasbt0,
                      htlr_handle** out);
 void htlr_cuda_destroy(htlr_handle* h);
+/* Destroyed handles leave their device memory in a per-process cache for the next create on the same device
+ * (bounded by HTLR_CACHE_MB, default 4096 MB; 0 disables). This returns it to the driver. */
+void htlr_cuda_release_cache(void);
 
 /* Replaces n_iters passes of the loop body of `Fit::StartSampling` (gibbs.cpp:57-125). Call in chunks
  * (<= 256 keeps R interruptible). stats (nullable) receives n_iters entries. Synchronises before returning. */
@@ -142,6 +151,18 @@ int htlr_cuda_fetch(htlr_handle* h, double* mcdeltas, double* mcsigmasbt, double
                     double* mclogw, double* mcloglike, double* mcuvar, double* mchmcrej,
                     double* ddnloglike);
 int32_t htlr_cuda_hist_len(const htlr_handle* h);
+
+/* Pipelined form of run + fetch for hosts that want the trace download hidden behind the sampling
+ * (`Fit::OutputR` copies `mcdeltas` etc. after the loop, gibbs.cpp:128-152; here the copy of slice i overlaps
+ * iteration i+1..): waits until the first `upto_iters` iterations (counted since create, enqueued earlier with
+ * htlr_cuda_run_async) have finished — work enqueued after them keeps running —, then copies
+ *  - the per-iteration stats of iterations [stats_from, upto_iters) into `stats` (nullable), and
+ *  - every trace slice that is complete and was not copied by an earlier collect call on this handle into the
+ *    caller's FULL-SIZE arrays (layout of htlr_cuda_fetch; any pointer may be NULL; pass the same arrays to
+ *    every call). After a collect with upto_iters = iters_h + iters_rmc the arrays equal htlr_cuda_fetch's. */
+int htlr_cuda_collect(htlr_handle* h, int32_t upto_iters, int32_t stats_from, htlr_iter_stats* stats,
+                      double* mcdeltas, double* mcsigmasbt, double* mcvardeltas, double* mclogw,
+                      double* mcloglike, double* mcuvar, double* mchmcrej);
 
 /* One call = htlr_fit_helper's body: create, run everything (in chunks of 256, calling `tick` after each
  * chunk with the iterations done so far and the latest stats; a non-zero return from tick aborts — the

@@ -144,12 +144,15 @@ def test_run_past_the_end_is_refused():
 
 def test_single_call_entry_point_with_tick_callback():
     """htlr_cuda_fit (the whole of htlr_fit_helper in one C call): same chain as create/run/fetch, the tick callback
-    sees every chunk, and a non-zero return aborts with HTLR_E_STATE."""
+    sees every unit of the pipelined run, and a non-zero return aborts with HTLR_E_STATE."""
     import ctypes
     import htlr_b200
     from htlr_b200 import _lib
     args = problem(70, 40, 3, seed=6, iters_rmc=300, iters_h=20, leap_L=4, leap_L_h=2)
-    ref = htlr_b200.htlr_fit_helper(**args, seed=9)
+    plain = htlr_b200.Sampler(**args, seed=9)     # blocking create / run / fetch
+    plain.run(320)
+    ref = plain.fetch()
+    plain.close()
     L = _lib.lib()
     s = htlr_b200.Sampler(**dict(args, iters_rmc=1, iters_h=0), seed=9)   # only to borrow a filled htlr_cfg
     cfg = s.cfg
@@ -173,8 +176,13 @@ def test_single_call_entry_point_with_tick_callback():
                          p(out["mcdeltas"]), p(out["mcsigmasbt"]), p(out["mcvardeltas"]), p(out["mclogw"]),
                          p(out["mcloglike"]), p(out["mcuvar"]), p(out["mchmcrej"]), p(out["ddn"]), err, 256)
     assert rc == 0, err.value
-    assert [d for d, _, _ in seen] == [256, 320] and [c for _, c, _ in seen] == [256, 64]   # chunks of 256 (gibbs.cpp:124)
-    assert np.array_equal(out["mcdeltas"], ref["mcdeltas"]) and np.array_equal(out["mcuvar"], ref["mcuvar"].ravel())
+    # units of 8 iterations: far inside the reference's poll interval of 256 (gibbs.cpp:124)
+    assert [d for d, _, _ in seen] == list(range(8, 321, 8)) and all(c == 8 for _, c, _ in seen)
+    for k in ("mcdeltas", "mcsigmasbt", "mcvardeltas"):
+        assert np.array_equal(out[k], ref[k]), k
+    for k in ("mclogw", "mcloglike", "mcuvar", "mchmcrej"):
+        assert np.array_equal(out[k], ref[k].ravel()), k
+    assert np.array_equal(out["ddn"], ref["mc.param"]["DDNloglike"].ravel())
     cb2 = _lib.TICK_FN(lambda user, done, stats, n_chunk: 1)
     rc = L.htlr_cuda_fit(ctypes.byref(cfg), p(X), 70, p(ym), p(yb, _lib.c_lp), p(d0), p(s0), None, cb2, None,
                          p(out["mcdeltas"]), p(out["mcsigmasbt"]), p(out["mcvardeltas"]), p(out["mclogw"]),
