@@ -38,7 +38,10 @@ Rcpp::List htlr_fit_helper(int p, int K, int n, arma::mat& X, arma::mat& ymat, a
         for (int i = 0; i < chunk; ++i, ++printed)  // gibbs.cpp:119-121
           Rprintf("Iter%4d: deviance=%5.3f, logw=%6.2f, nuvar=%3.0f, hmcrej=%4.2f\n", printed - iters_h,
                   -st[i].loglike / n, st[i].logw, st[i].uvar, st[i].rej);
-      R_CheckUserInterrupt();  // gibbs.cpp:124 (every 256 iterations = every chunk)
+      // gibbs.cpp:124 polls R_CheckUserInterrupt() every 256 iterations; here every pipelined unit of 8. The
+      // throwing form unwinds through ~CudaFit, which waits for the iterations already in flight and frees the
+      // device state (a longjmp out of R_CheckUserInterrupt would skip that).
+      Rcpp::checkUserInterrupt();
       return false;
     });
     o = fit.Output();
