@@ -503,20 +503,30 @@ __global__ void __launch_bounds__(kFT, 1) k_traj(Geom g, Bufs b, FusedGeom fg, i
     {
       double l[KT];
       if (CL) {
-        // thread <-> row: the partials sit in the owners' shared memory; every load is issued before the
-        // first add, the adds run in block order
-        if (ct < nrows) {
-          const uint32_t base = smem_u32(lp_own) + (uint32_t)(row0 + ct) * 8u;
+        // the partials sit in the owners' shared memory. thread <-> (row, class) item: one round of remote loads
+        // for all classes at once (a thread per row would pay one distributed-shared-memory round trip per
+        // class); every load is issued before the first add, the adds run in block order
+        auto gather = [&](int ii, int k) {
+          const uint32_t base = smem_u32(lp_own) + (uint32_t)(k * n_e + row0 + ii) * 8u;
+          double pv[kClMax];
 #pragma unroll
-          for (int k = 0; k < KT; ++k) {
-            double pv[kClMax];
+          for (int qq = 0; qq < kClMax; ++qq) pv[qq] = (qq < gact) ? ld_dsmem(map_to_cta(base, (uint32_t)qq)) : 0.0;
+          double a = pv[0];
 #pragma unroll
-            for (int qq = 0; qq < kClMax; ++qq)
-              pv[qq] = (qq < gact) ? ld_dsmem(map_to_cta(base + (uint32_t)(k * n_e) * 8u, (uint32_t)qq)) : 0.0;
-            double a = pv[0];
+          for (int qq = 1; qq < kClMax; ++qq) a += pv[qq];
+          return rowc[(size_t)ii * (2 * KT + 2) + k] + a;
+        };
+        if (KT == 1) {
+          if (ct < nrows) l[0] = gather(ct, 0);
+        } else {
+          for (int item = ct; item < nrows * KT; item += kCT) {
+            const int k = item / nrows, ii = item - k * nrows;
+            dl[ii * KT + k] = gather(ii, k);
+          }
+          named_bar(kBarCompute, kCT);
+          if (ct < nrows) {
 #pragma unroll
-            for (int qq = 1; qq < kClMax; ++qq) a += pv[qq];
-            l[k] = rowc[(size_t)ct * (2 * KT + 2) + k] + a;
+            for (int k = 0; k < KT; ++k) l[k] = dl[ct * KT + k];
           }
         }
       } else {

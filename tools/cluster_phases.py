@@ -3,7 +3,7 @@ import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import htlr_b200
 from tests.helpers import problem
-for n, C, u in ((62, 2, 208), (200, 2, 256), (500, 4, 64), (1000, 3, 128), (1000, 3, 16)):
+for n, C, u in ((62, 2, 208), (62, 2, 16), (200, 2, 256), (500, 4, 12), (500, 4, 64), (500, 2, 12), (1000, 3, 128), (1000, 3, 16)):
     args = problem(n, u - 1, C, seed=1, iters_rmc=60, iters_h=0, leap_L=50, hmc_sgmcut=0.0, init="zero")
     s = htlr_b200.Sampler(**args, seed=3, algo=3)
     s.run(5)
