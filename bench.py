@@ -321,6 +321,7 @@ def measure_e2e(torch, wl, steps, device, chain_seed, dist):
     H = steps + 1
     d2h = 8 * (nvar * K * H + 2 * nvar * H + 4 * H + nvar)
     assert np.isfinite(out["mcloglike"]).all()
+    measure_e2e.calls_s = [round(t, 5) for t in times]
     return (t1 - t0), h2d / steps, d2h / steps, warm_iters
 
 
@@ -633,7 +634,9 @@ def main():
                        "algorithm": "two-sweep (reference structure)" if a.algo == 1 else "fused one-sweep persistent trajectory kernel", "mean_nuvar": u, "hmc_reject": res["rej"]},
             "e2e": {"value": e2e_value, "unit": "it/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "what": "htlr_fit_helper() with pinned host buffers: H2D of X/ymat/state, %d sampling iterations "
-                            "(after %d warm-up), D2H of the full trace; median of 3 calls" % (a.steps, e2e_warm)},
+                            "(after %d warm-up), D2H of the full trace (pipelined behind the sampling, units of 8 "
+                            "iterations); median of 3 calls" % (a.steps, e2e_warm),
+                    "calls_s": getattr(measure_e2e, "calls_s", None)},
             "gpu_launches": res["launches"],
             "clocks": clk,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",

@@ -73,8 +73,8 @@ __global__ void __launch_bounds__(1024) k_select(Geom g, Bufs b) {
   const int seg = (((nvar + 31) / 32) + 31) & ~31;            // features per warp, a multiple of 32
   const int j0 = min(nvar, w * seg), j1 = min(nvar, j0 + seg);
   int cnt = 0;
-#pragma unroll 4
-  for (int j = j0 + lane; j - lane < j1; j += 32) {
+#pragma unroll 16
+  for (int j = j0 + lane; j - lane < j1; j += 32) {   // 16 loads in flight: two or three L2 round trips per segment
     const bool f = j < j1 && b.sigmasbt[j] > cut;
     cnt += __popc(__ballot_sync(0xffffffffu, f));
   }
@@ -294,15 +294,15 @@ __global__ void __launch_bounds__(256) k_softmax(Geom g, Bufs b, int what, const
 #pragma unroll
     for (int k = 0; k < KM; ++k) {
       if (k < K) {
-        // slots summed in order, 8 loads in flight at a time (one L2 round trip per 8 slots, not per slot)
+        // slots summed in order, 16 loads in flight at a time (one L2 round trip per 16 slots, not per slot)
         double sacc = 0;
-        for (int s0 = 0; s0 < cs.slots; s0 += 8) {
-          double pv[8];
+        for (int s0 = 0; s0 < cs.slots; s0 += 16) {
+          double pv[16];
 #pragma unroll
-          for (int q = 0; q < 8; ++q)
+          for (int q = 0; q < 16; ++q)
             pv[q] = (s0 + q < cs.slots) ? __ldcg(&b.lvpart[((int64_t)(s0 + q) * K + k) * g.n_s + i]) : 0.0;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) sacc += pv[q];
+          for (int q = 0; q < 16; ++q) sacc += pv[q];
         }
         const int64_t e = (int64_t)k * g.n_s + i;
         if (what == 0) {

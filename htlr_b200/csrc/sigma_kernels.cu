@@ -58,6 +58,18 @@ __global__ void __launch_bounds__(256) k_tail_t(Geom g, Bufs b) {
   for (int j = tid; j < nvar; j += nt) {
     const int r = b.posof[j];
     double vd = b.var_deltas[j];
+    // the gamma draw depends on nothing loaded here: it runs while posof / var_deltas are on their way (the
+    // branch on r below would otherwise stall the thread for an L2 round trip first)
+    double gm = 1.0;
+    if (j >= 1) {
+      if (ctl->rng_mode == 1) {
+        const long long at = ctl->cur_gam + (j - 1);
+        if (at >= ctl->n_gam) { set_err(ctl, kErrInjectGammas, 0); gm = 1.0; }
+        else gm = b.inj_gam[at];
+      } else {
+        gm = rng.gamma(ctl->step, (uint32_t)j, shape);
+      }
+    }
     if (accept && r >= 0) {
       vd = b.vdc[r];
       b.var_deltas[j] = vd;
@@ -71,14 +83,6 @@ __global__ void __launch_bounds__(256) k_tail_t(Geom g, Bufs b) {
     }
     double sg = b.sigmasbt[j];
     if (j >= 1) {
-      double gm;
-      if (ctl->rng_mode == 1) {
-        const long long at = ctl->cur_gam + (j - 1);
-        if (at >= ctl->n_gam) { set_err(ctl, kErrInjectGammas, 0); gm = 1.0; }
-        else gm = b.inj_gam[at];
-      } else {
-        gm = rng.gamma(ctl->step, (uint32_t)j, shape);
-      }
       sg = (1.0 / gm * (ctl->alpha * w + vd) / 2.0);
       b.sigmasbt[j] = sg;
     }
