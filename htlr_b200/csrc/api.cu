@@ -60,11 +60,8 @@ struct NcclApi {
   std::string error;
   bool ok = false;
 };
-NcclApi& nccl_api() {
-  static NcclApi api;
-  static bool tried = false;
-  if (tried) return api;
-  tried = true;
+NcclApi load_nccl() {
+  NcclApi api;
   void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
   if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
   if (!lib) {
@@ -78,6 +75,10 @@ NcclApi& nccl_api() {
   api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
   api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.GetErrorString;
   if (!api.ok) api.error = "libnccl.so.2 lacks an expected symbol";
+  return api;
+}
+NcclApi& nccl_api() {
+  static NcclApi api = load_nccl();   // thread-safe one-time initialisation
   return api;
 }
 NcclApi& nccl_need() {

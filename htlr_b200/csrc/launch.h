@@ -2,12 +2,26 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstddef>
 #include <cstdint>
 
 #include "common.cuh"
 
 namespace htlr {
+
+// cudaFuncSetAttribute applies to the CURRENT device only, and a process may drive several GPUs (one host thread
+// per chain / fold): one "configured" bit per device for every kernel instantiation that needs opt-in shared memory.
+struct PerDeviceOnce {
+  std::atomic<unsigned long long> done{0};
+  static unsigned long long bit() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return 1ull << (dev & 63);
+  }
+  bool needed() const { return (done.load(std::memory_order_acquire) & bit()) == 0; }
+  void mark() { done.fetch_or(bit(), std::memory_order_acq_rel); }
+};
 
 // Geometry of the sweep kernels, fixed at create time (grids never depend on the restricted-set size,
 // which only the device knows; surplus blocks exit immediately).

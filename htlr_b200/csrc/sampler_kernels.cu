@@ -689,10 +689,10 @@ void launch_lv_sweep(const Geom& g, const Bufs& b, int mode, const int* idx, con
   dim3 grid(g.lv_cs, g.lv_rt);
   const size_t smem = (size_t)kLvChunk * (g.K * sizeof(double) + sizeof(int64_t));   // <= 36 KB at K = 16... see below
   DISPATCH_K(g.K, {
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.needed()) {
       cudaFuncSetAttribute(k_lv_sweep<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
-      configured = true;
+      configured.mark();
     }
     k_lv_sweep<KT><<<grid, 256, smem, st>>>(g, b, mode, idx, cnt, coef_global);
   });
@@ -707,10 +707,10 @@ void launch_grad_sweep(const Geom& g, const Bufs& b, const int* idx, const int* 
   dim3 grid(g.g_gx, g.g_rt);
   const size_t smem = (size_t)g.K * g.g_tr * sizeof(double);   // <= 64 KB by the choice of g_tr
   DISPATCH_K(g.K, {
-    static bool configured = false;   // per instantiation: the residual tile can exceed the 48 KB default
-    if (!configured) {
+    static PerDeviceOnce configured;   // per instantiation: the residual tile can exceed the 48 KB default
+    if (configured.needed()) {
       cudaFuncSetAttribute(k_grad_sweep<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-      configured = true;
+      configured.mark();
     }
     k_grad_sweep<KT><<<grid, 256, smem, st>>>(g, b, idx, cnt, R, gout);
   });

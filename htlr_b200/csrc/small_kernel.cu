@@ -281,12 +281,12 @@ __global__ void __launch_bounds__(kST, 1) k_traj_small(Geom g, Bufs b, int L, in
 namespace {
 template <int KT>
 cudaError_t launch_small_k(const Geom& g, const Bufs& b, int L, int smem_bytes, int u_max, cudaStream_t st) {
-  static bool configured = false;
+  static PerDeviceOnce configured;
   auto kern = k_traj_small<KT>;
-  if (!configured) {
+  if (configured.needed()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return e;
-    configured = true;
+    configured.mark();
   }
   kern<<<1, kST, smem_bytes, st>>>(g, b, L, smem_bytes / (int)sizeof(double), u_max);
   return cudaGetLastError();

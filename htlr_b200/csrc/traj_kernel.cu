@@ -648,16 +648,16 @@ namespace {
 
 template <int KT, int NRP, int GW, bool CL>
 cudaError_t launch_one(const Geom& g, const Bufs& b, const FusedGeom& fg, int L, cudaStream_t st) {
-  static bool configured = false;
+  static PerDeviceOnce configured;
   auto kern = k_traj<KT, NRP, GW, CL>;
-  if (!configured) {
+  if (configured.needed()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fg.smem_bytes_max);
     if (e != cudaSuccess) return e;
     if (CL && fg.cl > 8) {
       e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
       if (e != cudaSuccess) return e;
     }
-    configured = true;
+    configured.mark();
   }
   Geom gg = g;
   Bufs bb = b;

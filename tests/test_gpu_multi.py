@@ -93,3 +93,35 @@ def test_row_sharded_device_rng_matches_single_gpu():
         assert np.array_equal(out["mchmcrej"], ref["mchmcrej"])
         assert relerr(out["mcdeltas"], ref["mcdeltas"]) < 1e-8
         assert relerr(out["mcloglike"], ref["mcloglike"]) < 1e-8
+
+
+def test_one_process_drives_chains_on_two_devices():
+    """Chains / CV folds may also be spread over the GPUs from ONE process (a host thread per device): kernel
+    attributes (opt-in shared memory, cluster size) are per device, the device-memory cache is keyed by device, and
+    the same key gives the same chain on either GPU."""
+    import threading
+    import htlr_b200
+    _need_two_gpus()
+    cases = [problem(900, 700, 3, seed=3, iters_h=4, iters_rmc=12, leap_L=10, leap_L_h=3, hmc_sgmcut=0.0),   # grid mode
+             problem(62, 300, 2, seed=4, iters_h=4, iters_rmc=12, leap_L=10, leap_L_h=3),                    # small / cluster
+             problem(300, 40, 17, seed=5, iters_h=2, iters_rmc=6, leap_L=4, leap_L_h=2)]                     # K = 16: generic kernels
+    out = {}
+
+    def chain(dev, ci):
+        s = htlr_b200.Sampler(**cases[ci], seed=100 + ci, device=dev)
+        s.run(cases[ci]["iters_h"] + cases[ci]["iters_rmc"])
+        out[(dev, ci)] = s.fetch()
+        s.close()
+    for ci in range(len(cases)):
+        chain(0, ci)                       # device 0 first: configures every kernel there
+    threads = [threading.Thread(target=lambda: [chain(1, ci) for ci in range(len(cases))]),
+               threading.Thread(target=lambda: [chain(0, ci) for ci in reversed(range(len(cases)))])]
+    first = {k: v for k, v in out.items()}
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for ci in range(len(cases)):
+        for k in ("mcdeltas", "mcsigmasbt", "mcloglike", "mcuvar", "mchmcrej"):
+            assert np.array_equal(out[(1, ci)][k], first[(0, ci)][k]), (ci, k)
+            assert np.array_equal(out[(0, ci)][k], first[(0, ci)][k]), (ci, k)
