@@ -74,3 +74,17 @@ def test_collect_without_marks_falls_back_to_a_full_sync():
     for k in TRACE:
         assert np.array_equal(out[k], ref[k]), k
     s.close()
+
+
+@pytest.mark.parametrize("over", [dict(thin=3), dict(ptype="ghs", alpha=1.0), dict(ptype="neg", alpha=2.0, thin=2),
+                                  dict(eta=0.5)], ids=["thin3", "ghs", "neg-thin2", "logw-ars"])
+def test_pipelined_helper_with_thinning_and_the_other_priors(over):
+    """The trace slice index does not depend on how the iterations were enqueued (units of 8 thin-groups, graphs of
+    8 iterations only when thin = 1): thinning, ARS-based priors and the logw update give the blocking run's trace."""
+    import htlr_b200
+    args = problem(80, 120, 3, seed=12, iters_h=5, iters_rmc=21, leap_L=5, leap_L_h=2, keep_warmup_hist=True,
+                   init="random", **over)
+    ref, _ = blocking(args, seed=33)
+    out = htlr_b200.htlr_fit_helper(**args, seed=33)
+    for k in TRACE:
+        assert np.array_equal(out[k], ref[k]), k
