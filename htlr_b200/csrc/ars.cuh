@@ -1,7 +1,10 @@
-// Adaptive rejection sampling, one WARP per draw: lane h owns tangent hull h (so at most 32 hulls —
-// the reference allows 1000, `ars.h:61`, but its own targets never need more than ~13; with a full
-// table insertion simply stops, exactly what the reference does when `no_hulls_ == max_nhull_`,
-// ars.cpp:26, so this is the reference engine run with max_nhull = 32).
+// Adaptive rejection sampling, one GROUP of W lanes per draw (W = 32: a warp; W = 16: two draws per warp): lane h of
+// the group owns tangent hull h (so at most W hulls — the reference allows 1000, `ars.h:61`, but its own targets
+// never need more than ~13; with a full table insertion simply stops, exactly what the reference does when
+// `no_hulls_ == max_nhull_`, ars.cpp:26, so this is the reference engine run with max_nhull = W). Every scalar of
+// the engine is computed redundantly by all lanes of the group and the FP64 pipe is what bounds the kernel, so
+// two draws per warp (the halves run the same code on different features, diverging only when their accept /
+// reject histories differ) nearly halve the cost per draw.
 //
 // Replaces, for n = 1 draw (the only way gibbs.cpp uses it, gibbs.cpp:344-345, 358, 367):
 //   ARS::ARS         src/ars.cpp:204-242   first tangent at x0, error if logf(x0) is not finite
@@ -9,8 +12,8 @@
 //   update_hulls     src/ars.cpp:22-119    insert a tangent, fix the two neighbours
 //   ARS::Sample      src/ars.cpp:259-318   pick hull, pick point, squeeze test, accept test
 //   sample_disc / sample_elin / logint_elin / interc   src/ars.cpp:334-462
-// All scalar quantities are warp-uniform (every lane evaluates the same expression on the same
-// operands); per-hull fields live one per lane and are broadcast with shuffles. The cumulative hull
+// All scalar quantities are group-uniform (every lane evaluates the same expression on the same
+// operands); per-hull fields live one per lane and are broadcast with shuffles inside the group. The cumulative hull
 // weights are summed left to right like the reference so that, fed the same uniforms, the draw
 // matches the CPU engine to the last few ulps of libm.
 //
@@ -32,7 +35,6 @@ enum ArsStatus : int {
   kArsStuck = 5,         // guard: more than kArsMaxTries proposals
 };
 
-constexpr int kArsCap = 32;
 constexpr int kArsMaxTries = 4096;
 constexpr double kArsStepout = 10.0, kArsTolD = 1e-5, kArsTolDD = 1e-5;
 
@@ -42,8 +44,6 @@ constexpr double kArsStepout = 10.0, kArsTolD = 1e-5, kArsTolDD = 1e-5;
 __device__ __noinline__ double ars_exp(double x) { return exp(x); }
 __device__ __noinline__ double ars_log(double x) { return log(x); }
 
-__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
-__device__ __forceinline__ int shfl_i(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
 // ars.cpp:424-450
 __device__ __forceinline__ double ars_logint(double f, double df, double t, double lo, double hi) {
@@ -101,20 +101,28 @@ struct ArsHull {
   int left, right;
 };
 
-template <class Eval, class Unif>
+template <class Eval, class Unif, int W = 32>
 struct ArsWarp {
+  static_assert(W == 32 || W == 16, "a group is a warp or half a warp");
+  static constexpr int kArsCap = W;   // hull table size; also the "no right neighbour" sentinel
   ArsHull H;  // this lane's hull
   int nh;
-  int lane;
+  int lane;        // lane within the group
+  int base;        // first lane of the group within the warp
+  unsigned mask;   // the group's lanes
   Eval& ev;
   Unif& un;
   int n_eval, n_unif;
 
   __device__ ArsWarp(Eval& e, Unif& u) : ev(e), un(u) {
-    lane = threadIdx.x & 31;
+    lane = threadIdx.x & (W - 1);
+    base = (threadIdx.x & 31) & ~(W - 1);
+    mask = W == 32 ? 0xffffffffu : (0xffffu << base);
     nh = 0;
     n_eval = n_unif = 0;
   }
+  __device__ __forceinline__ double shfl_d(double v, int src) const { return __shfl_sync(mask, v, src, W); }
+  __device__ __forceinline__ int shfl_i(int v, int src) const { return __shfl_sync(mask, v, src, W); }
 
   __device__ __forceinline__ void relog() { H.lw = ars_logint(H.f, H.df, H.t, H.lo, H.hi); }
 
@@ -194,7 +202,7 @@ struct ArsWarp {
       // sample_disc, ars.cpp:334-356: max-shifted weights, cumulative sum left to right
       double mx = lane < nh ? H.lw : -INFINITY;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      for (int o = W / 2; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(mask, mx, o, W));
       double e = lane < nh ? ars_exp(H.lw - mx) : 0.0;
       double acc = 0.0, cw = 0.0;
       for (int i = 0; i < nh; ++i) {
@@ -205,7 +213,7 @@ struct ArsWarp {
       if (!un.next(u)) return kArsNoUniforms;
       ++n_unif;
       u *= acc;
-      unsigned hit = __ballot_sync(0xffffffffu, lane < nh && u <= cw);
+      const unsigned hit = __ballot_sync(mask, lane < nh && u <= cw) >> base;   // bits of this group only
       h = hit ? (__ffs(hit) - 1) : nh - 1;
       // sample_elin, ars.cpp:359-417
       const double lo = shfl_d(H.lo, h), hi = shfl_d(H.hi, h), dh = shfl_d(H.df, h);

@@ -124,16 +124,18 @@ __global__ void __launch_bounds__(256) k_tail_t(Geom g, Bufs b) {
   }
 }
 
-// ghs / neg: one warp per feature, ARS on x = log sigma^2_j from x0 = log(var_deltas_j / K).
-// 3 blocks per SM (80 registers, a few spilled words): measured 6-7 % faster than 2 blocks at 108 registers; 4 blocks
-// add nothing. The engine is bound by the FP64 pipe doing warp-uniform scalar work in all 32 lanes.
+// ghs / neg: ARS on x = log sigma^2_j from x0 = log(var_deltas_j / K), kArsGroup lanes per feature (two features per
+// warp: see ars.cuh).
+constexpr int kArsGroup = 16;
+// 3 blocks per SM (80 registers): measured 6-7 % faster than 2 blocks at 108 registers; 4 blocks add nothing. The
+// engine is bound by the FP64 pipe doing group-uniform scalar work in every lane.
 __global__ void __launch_bounds__(256, 3) k_sigma_ars(Geom g, Bufs b) {
   Ctl* ctl = b.ctl;
   const int p = ctl->p;
-  const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int lane = threadIdx.x & (kArsGroup - 1);
+  const int grp = (blockIdx.x * blockDim.x + threadIdx.x) / kArsGroup, ngrp = (gridDim.x * blockDim.x) / kArsGroup;
   const double log_aw = ctl->logw + log(ctl->alpha);
-  for (int q = warp; q < p; q += nwarps) {
+  for (int q = grp; q < p; q += ngrp) {
     const int j = q + 1;
     SgmTarget tg{ctl->ptype, b.var_deltas[j], (double)ctl->K, ctl->alpha, log_aw};
     const double x0 = log(tg.v / tg.K);
@@ -147,7 +149,7 @@ __global__ void __launch_bounds__(256, 3) k_sigma_ars(Geom g, Bufs b) {
         un.u = b.inj_ars + blk * ctl->ars_width;
         un.n = blk < ctl->n_ars_blocks ? ctl->ars_width : 0;
       }
-      ArsWarp<SgmTarget, ArsUniforms> ars(tg, un);
+      ArsWarp<SgmTarget, ArsUniforms, kArsGroup> ars(tg, un);
       status = ars.sample(x0, x);
     }
     if (status != kArsOk) {
@@ -221,21 +223,21 @@ __global__ void __launch_bounds__(256) k_ars_batch(int kind, int m, const double
                                                     double log_aw, const double* uniforms, int width,
                                                     unsigned long long seed, unsigned long long step, double* x_out,
                                                     int* n_unif, int* n_eval, int* status_out) {
-  const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (int q = warp; q < m; q += nwarps) {
+  const int lane = threadIdx.x & (kArsGroup - 1);
+  const int grp = (blockIdx.x * blockDim.x + threadIdx.x) / kArsGroup, ngrp = (gridDim.x * blockDim.x) / kArsGroup;
+  for (int q = grp; q < m; q += ngrp) {
     SgmTarget tg{kind, vard[q], K, alpha, log_aw};
     const double x0 = log(tg.v / tg.K);
     double x = NAN;
     int status, nu, ne;
     if (uniforms) {
       ArsArrayUniforms un{uniforms + (long long)q * width, width, 0};
-      ArsWarp<SgmTarget, ArsArrayUniforms> ars(tg, un);
+      ArsWarp<SgmTarget, ArsArrayUniforms, kArsGroup> ars(tg, un);
       status = ars.sample(x0, x);
       nu = ars.n_unif; ne = ars.n_eval;
     } else {
       ArsKeyedUniforms un{seed, step, kRngArs, (uint32_t)(q + 1), 0u};
-      ArsWarp<SgmTarget, ArsKeyedUniforms> ars(tg, un);
+      ArsWarp<SgmTarget, ArsKeyedUniforms, kArsGroup> ars(tg, un);
       status = ars.sample(x0, x);
       nu = ars.n_unif; ne = ars.n_eval;
     }
@@ -269,7 +271,8 @@ void launch_sigma(const Geom& g, const Bufs& b, cudaStream_t st) {
 void launch_tail_t(const Geom& g, const Bufs& b, cudaStream_t st) { k_tail_t<<<g.e_grid, 256, 0, st>>>(g, b); }
 void launch_sigma_ars(const Geom& g, const Bufs& b, cudaStream_t st) {
   const int p = g.nvar - 1;
-  int blocks = (p + 7) / 8;
+  const int per_block = 256 / kArsGroup;   // features in flight per block
+  int blocks = (p + per_block - 1) / per_block;
   if (blocks > g.sm_count * 8) blocks = g.sm_count * 8;
   if (blocks < 1) blocks = 1;
   k_sigma_ars<<<blocks, 256, 0, st>>>(g, b);
@@ -279,7 +282,8 @@ void launch_logw(const Geom& g, const Bufs& b, cudaStream_t st) { k_logw<<<1, 10
 void launch_ars_standalone(int kind, int m, const double* vard, double K, double alpha, double log_aw,
                            const double* uniforms, int width, unsigned long long seed, unsigned long long step,
                            double* x_out, int* n_unif, int* n_eval, int* status, cudaStream_t st) {
-  int blocks = (m + 7) / 8;
+  const int per_block = 256 / kArsGroup;
+  int blocks = (m + per_block - 1) / per_block;
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
   k_ars_batch<<<blocks, 256, 0, st>>>(kind, m, vard, K, alpha, log_aw, uniforms, width, seed, step, x_out, n_unif,

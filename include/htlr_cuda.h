@@ -115,7 +115,7 @@ typedef struct htlr_profile {
   int64_t sweep_launches;
   double total_ms;        /* all kernels of the timed thin-steps */
   int64_t kernel_launches;/* launches issued by this library since create / reset */
-  double sigma_ms;        /* per-feature variance update (gamma draws or warp-per-feature ARS) */
+  double sigma_ms;        /* per-feature variance update (gamma draws or warp-collective ARS) */
   /* fused trajectory kernel, block 0's view (SM cycle counter / clock rate): time in the column sweeps,
    * waiting at the two grid-wide barriers of each leapfrog step, and in the row phase between them */
   double fused_sweep_ms, fused_barrier_ms, fused_rowphase_ms;
