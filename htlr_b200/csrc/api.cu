@@ -6,6 +6,7 @@
 #include <nccl.h>   // types and enums only: the library itself is bound at run time (see NcclApi below)
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstddef>
 #include <cstdio>
@@ -47,6 +48,52 @@ struct CudaFail {
 #define FAIL(code, text) throw CudaFail{code, text}
 
 int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+// The few device attributes the library needs, read once per device with cudaDeviceGetAttribute:
+// cudaGetDeviceProperties costs 2.5 ms per call on this platform and now and then 15-180 ms, which showed up as
+// outliers of a whole fit's end-to-end time.
+struct DevInfo {
+  int major = 0, sm_count = 0, smem_optin = 0, coop = 0;
+  bool ok = false;
+};
+const DevInfo& dev_info(int device) {
+  static std::mutex mu;
+  static DevInfo table[64];
+  std::lock_guard<std::mutex> lk(mu);
+  DevInfo& d = table[device & 63];
+  if (!d.ok) {
+    CU(cudaDeviceGetAttribute(&d.major, cudaDevAttrComputeCapabilityMajor, device));
+    CU(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, device));
+    CU(cudaDeviceGetAttribute(&d.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    CU(cudaDeviceGetAttribute(&d.coop, cudaDevAttrCooperativeLaunch, device));
+    d.ok = true;
+  }
+  return d;
+}
+
+// HTLR_TRACE_CREATE=1: wall-clock stamps of the phases of htlr_cuda_create on stderr (where does a slow create go?)
+struct CreateTrace {
+  bool on;
+  std::chrono::steady_clock::time_point t0, last;
+  std::string line;
+  CreateTrace() {
+    const char* e = std::getenv("HTLR_TRACE_CREATE");
+    on = e && std::atoi(e) > 0;
+    t0 = last = std::chrono::steady_clock::now();
+  }
+  void mark(const char* what) {
+    if (!on) return;
+    const auto now = std::chrono::steady_clock::now();
+    char buf[96];
+    snprintf(buf, sizeof(buf), " %s=%.2f", what, std::chrono::duration<double, std::milli>(now - last).count());
+    line += buf;
+    last = now;
+  }
+  ~CreateTrace() {
+    if (on) fprintf(stderr, "[htlr create ms]%s total=%.2f\n", line.c_str(),
+                    std::chrono::duration<double, std::milli>(last - t0).count());
+  }
+};
 
 // NCCL is bound with dlopen on first use instead of being a link-time dependency: only the row-sharded path
 // needs it, and a process that also hosts another NCCL user (a PyTorch that bundles its own, newer libnccl.so.2)
@@ -461,14 +508,19 @@ void do_create(const htlr_cfg* cfg, const double* X, int64_t ldx, const double* 
   if (!X || !ymat || !ybase || !deltas0 || !sigmasbt0) FAIL(HTLR_E_ARG, "null input array");
   if (ldx < c.n) FAIL(HTLR_E_ARG, "ldx < n");
   if (c.rng_mode != HTLR_RNG_DEVICE && c.rng_mode != HTLR_RNG_INJECT) FAIL(HTLR_E_ARG, "bad rng_mode");
+  CreateTrace tr;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     FAIL(HTLR_E_CUDA, "no CUDA device visible: this library has no CPU fallback");
   if (c.device < 0 || c.device >= ndev) FAIL(HTLR_E_ARG, "device ordinal out of range");
   CU(cudaSetDevice(c.device));
-  cudaDeviceProp prop;
-  CU(cudaGetDeviceProperties(&prop, c.device));
-  if (prop.major != 10) FAIL(HTLR_E_CUDA, std::string("built for sm_100a only; device is ") + prop.name);
+  const DevInfo& dev = dev_info(c.device);
+  if (dev.major != 10) {
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, c.device));
+    FAIL(HTLR_E_CUDA, std::string("built for sm_100a only; device is ") + prop.name);
+  }
+  tr.mark("props");
 
   h->cfg = c;
   h->sharded = c.nccl_comm != nullptr;
@@ -479,7 +531,7 @@ void do_create(const htlr_cfg* cfg, const double* X, int64_t ldx, const double* 
   Geom& g = h->g;
   g.n = n; g.nvar = nvar; g.K = K;
   g.n_s = (int)round_up(n, 16);
-  g.sm_count = prop.multiProcessorCount;
+  g.sm_count = dev.sm_count;
   g.lv_rt = (n + 511) / 512;
   g.lv_cs = (int)std::max<int64_t>(1, std::min<int64_t>((4 * g.sm_count + g.lv_rt - 1) / g.lv_rt, 1024));
   // residual tile of the gradient sweep: K * g_tr doubles <= 32 KB, so 6 blocks (48 warps) fit on an SM and keep
@@ -502,6 +554,7 @@ void do_create(const htlr_cfg* cfg, const double* X, int64_t ldx, const double* 
                    sizeof(Ctl) + 64 * 256;
     h->arena_reserve(bytes);
   }
+  tr.mark("stream+arena");
   // ---- data
   if (c.x_on_device) {
     if (ldx % 2) FAIL(HTLR_E_ARG, "device-resident X needs an even leading dimension");
@@ -514,6 +567,7 @@ void do_create(const htlr_cfg* cfg, const double* X, int64_t ldx, const double* 
                          cudaMemcpyHostToDevice, h->st));
     b.X = dX;
   }
+  tr.mark("X_enqueue");
   std::vector<int64_t> yb_host(n);
   if (c.x_on_device) CU(cudaMemcpy(yb_host.data(), ybase, n * sizeof(int64_t), cudaMemcpyDeviceToHost));
   else std::memcpy(yb_host.data(), ybase, n * sizeof(int64_t));
@@ -553,19 +607,18 @@ void do_create(const htlr_cfg* cfg, const double* X, int64_t ldx, const double* 
   b.vdc = h->dalloc<double>(nvar);
   b.g = h->dalloc<double>((size_t)nvar * K + 1);
   b.gpart = h->dalloc<double>((size_t)g.g_rt * nvar * K);
+  tr.mark("state_enqueue");
   // ---- trajectory algorithm
   {
     FusedGeom fgm{};
-    int coop = 0;
-    CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c.device));
-    const bool can = coop && !h->sharded && fused_plan(g, (int)prop.sharedMemPerBlockOptin, 0, &fgm);
+    const bool can = dev.coop && !h->sharded && fused_plan(g, dev.smem_optin, 0, &fgm);
     if ((c.algo == HTLR_ALGO_FUSED || c.algo == HTLR_ALGO_FUSED_CLUSTER || c.algo == HTLR_ALGO_CLUSTER_ONLY) && !can)
       FAIL(HTLR_E_ARG, "fused trajectory not applicable (needs K <= 4, a column tile in shared memory, one GPU)");
     h->fused = can && c.algo != HTLR_ALGO_TWO_SWEEP;
     h->fg = fgm;
     if (h->fused && c.algo != HTLR_ALGO_FUSED) {   // AUTO, FUSED_CLUSTER, CLUSTER_ONLY, FUSED_NO_SMALL, SMALL_FIRST
-      const int cl = fused_cluster_size(g, (int)prop.sharedMemPerBlockOptin);
-      h->has_cluster = cl > 0 && fused_plan(g, (int)prop.sharedMemPerBlockOptin, cl, &h->fgc);
+      const int cl = fused_cluster_size(g, dev.smem_optin);
+      h->has_cluster = cl > 0 && fused_plan(g, dev.smem_optin, cl, &h->fgc);
       if (h->has_cluster) {
         // Which flavour runs is decided on the device, per iteration, from the restricted-set size: both are
         // launched and the one that is not wanted returns at once (~2.5 us). Grid mode (148 blocks, exchange
@@ -582,7 +635,7 @@ void do_create(const htlr_cfg* cfg, const double* X, int64_t ldx, const double* 
     if ((c.algo == HTLR_ALGO_FUSED_CLUSTER || c.algo == HTLR_ALGO_CLUSTER_ONLY) && !h->has_cluster)
       FAIL(HTLR_E_ARG, "cluster-mode trajectory kernel not available on this device");
     h->use_cluster = h->fused && h->has_cluster;
-    h->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    h->smem_optin = dev.smem_optin;
     h->use_small = h->fused && small_applies(g) &&
                    (((c.algo == HTLR_ALGO_AUTO || c.algo == HTLR_ALGO_CLUSTER_ONLY) && g.n <= 256) ||
                     c.algo == HTLR_ALGO_SMALL_FIRST);
@@ -620,7 +673,9 @@ void do_create(const htlr_cfg* cfg, const double* X, int64_t ldx, const double* 
   ctl.init_all = 1;
   ctl.ars_width = c.ars_inject_width;
   CU(cudaMemcpyAsync(b.ctl, &ctl, sizeof(ctl), cudaMemcpyHostToDevice, h->st));
+  tr.mark("plan");
   CU(cudaStreamSynchronize(h->st));  // ctl / yb32 are host temporaries
+  tr.mark("sync_uploads");
 
   // ---- Fit::Fit tail + Fit::Initialize (gibbs.cpp:15, 519-530)
   launch_colsumsq(g, b.X, d_ddn, h->st);
@@ -642,6 +697,7 @@ void do_create(const htlr_cfg* cfg, const double* X, int64_t ldx, const double* 
   CU(cudaMemcpyAsync(h->ctl_int(offsetof(Ctl, init_all)), &zero, sizeof(int), cudaMemcpyHostToDevice, h->st));
   CU(cudaStreamSynchronize(h->st));
   CU(cudaGetLastError());
+  tr.mark("initialize");
 }
 
 void ensure_scratch(htlr_handle* h) {
@@ -1119,8 +1175,7 @@ int htlr_cuda_std(int32_t device, int32_t n, int32_t p, const double* A, int64_t
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
       FAIL(HTLR_E_CUDA, "no CUDA device visible: this library has no CPU fallback");
     CU(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    CU(cudaGetDeviceProperties(&prop, device));
+    const DevInfo& dev = dev_info(device);
     double *dA = nullptr, *dO = nullptr, *dm = nullptr, *ds = nullptr;
     auto cleanup = [&] { if (!on_device) { cudaFree(dA); cudaFree(dO); } cudaFree(dm); cudaFree(ds); };
     try {
@@ -1136,7 +1191,7 @@ int htlr_cuda_std(int32_t device, int32_t n, int32_t p, const double* A, int64_t
         src = dA; ls = n;
         if (A_std) { CU(cudaMalloc((void**)&dO, sizeof(double) * (size_t)n * p)); dst = dO; ld = n; }
       }
-      launch_std(n, p, src, ls, dst, ld, dm, ds, prop.multiProcessorCount, 0);
+      launch_std(n, p, src, ls, dst, ld, dm, ds, dev.sm_count, 0);
       CU(cudaDeviceSynchronize());
       CU(cudaGetLastError());
       if (!on_device && A_std)
