@@ -501,6 +501,7 @@ __global__ void __launch_bounds__(kFT, 1) k_traj(Geom g, Bufs b, FusedGeom fg, i
 
     // ---- sum the partials in block order, softmax, residual, log-likelihood (rows split over all blocks)
     {
+      const bool last_step = (s == L - 1);
       double l[KT];
       if (CL) {
         // the partials sit in the owners' shared memory. thread <-> (row, class) item: one round of remote loads
@@ -600,7 +601,7 @@ __global__ void __launch_bounds__(kFT, 1) k_traj(Geom g, Bufs b, FusedGeom fg, i
           const double nl = l[k] - lse;
           if (row_yb == k + 1) ll = nl;
           const double res = exp(nl) - rc[KT + k];
-          b.lv[(int64_t)k * n_s + i] = l[k];
+          if (last_step) b.lv[(int64_t)k * n_s + i] = l[k];   // the proposal's linear predictor: only the final one is state
           if (CL) {
             // push the new residual into every block's copy
             const uint32_t dst = smem_u32(Rs) + (uint32_t)(k * n_e + i) * 8u;
@@ -612,13 +613,17 @@ __global__ void __launch_bounds__(kFT, 1) k_traj(Geom g, Bufs b, FusedGeom fg, i
           }
         }
       }
-      ll = warp_sum(ll);
-      if (lane == 0) redsm[w] = ll;
-      named_bar(kBarCompute, kCT);
-      if (ct == 0) {
-        double t = 0;
-        for (int i = 0; i < kCW; ++i) t += redsm[i];
-        b.red[cta].c = t;
+      // UpdateLogLike (gibbs.cpp:254-261) is only read after the last step of the trajectory (CompNegEnergy,
+      // gibbs.cpp:418-419): the block reduction runs once per launch, not once per step
+      if (last_step) {
+        ll = warp_sum(ll);
+        if (lane == 0) redsm[w] = ll;
+        named_bar(kBarCompute, kCT);
+        if (ct == 0) {
+          double t = 0;
+          for (int i = 0; i < kCW; ++i) t += redsm[i];
+          b.red[cta].c = t;
+        }
       }
     }
     if (timer) { const long long t = clk(); atomicAdd(&ctl->ph_cycles[2], (unsigned long long)(t - tk0)); tk0 = t; }
