@@ -502,24 +502,44 @@ __global__ void __launch_bounds__(kFT, 1) k_traj(Geom g, Bufs b, FusedGeom fg, i
     // ---- sum the partials in block order, softmax, residual, log-likelihood (rows split over all blocks)
     {
       const bool last_step = (s == L - 1);
+      // Row softmax with one LANE per (row, class), class 0 (lv = 0) included: the C exponentials of a row, and
+      // then its K residual exponentials, run side by side instead of one after the other in one thread — the chain
+      // per row is exp, log, exp whatever K is (a thread per row needs 2K+1 exps and a log in sequence, ~160 cycles
+      // each). Rows of a warp: RPW = 32 / C; used when the block's row slice fits 16 warps that way.
+      constexpr int LPR = KT + 1;
+      constexpr int RPW = 32 / LPR;
+      // (only a cluster's slice of n > 1536 rows with K = 4 does not fit: the thread-per-row form below is compiled
+      // for that instantiation alone)
+      constexpr bool kMayNotFit = CL && KT == 4;
+      // Measured on one box (tools/timeline.py, us per iteration): K = 3 (config B) 235 -> 223 default cut, 569 -> 555
+      // full; K = 1 and K = 2 are slower this way (config A 163.6 -> 167.5, config C default 408 -> 419), so they
+      // keep the thread-per-row form.
+      constexpr int kByClassMinK = 3;
+      const bool by_class = KT >= kByClassMinK && (!kMayNotFit || fg.rpc <= kCW * RPW);
+      const int cr = lane / LPR, cc = lane - cr * LPR;       // this lane's row within the warp, and class
+      const int crow = w * RPW + cr;                          // row of the block's slice
+      const bool chave = by_class && lane < RPW * LPR && crow < nrows;
       double l[KT];
+      double lc = 0.0;   // by_class: this lane's linear predictor (class 0: 0)
+      // the partials of one (row, class) item of the cluster's blocks, added in block order
+      auto gather = [&](int ii, int k) {
+        const uint32_t base = smem_u32(lp_own) + (uint32_t)(k * n_e + row0 + ii) * 8u;
+        double pv[kClMax];
+#pragma unroll
+        for (int qq = 0; qq < kClMax; ++qq) pv[qq] = (qq < gact) ? ld_dsmem(map_to_cta(base, (uint32_t)qq)) : 0.0;
+        double a = pv[0];
+#pragma unroll
+        for (int qq = 1; qq < kClMax; ++qq) a += pv[qq];
+        return rowc[(size_t)ii * (2 * KT + 2) + k] + a;
+      };
       if (CL) {
-        // the partials sit in the owners' shared memory. thread <-> (row, class) item: one round of remote loads
-        // for all classes at once (a thread per row would pay one distributed-shared-memory round trip per
-        // class); every load is issued before the first add, the adds run in block order
-        auto gather = [&](int ii, int k) {
-          const uint32_t base = smem_u32(lp_own) + (uint32_t)(k * n_e + row0 + ii) * 8u;
-          double pv[kClMax];
-#pragma unroll
-          for (int qq = 0; qq < kClMax; ++qq) pv[qq] = (qq < gact) ? ld_dsmem(map_to_cta(base, (uint32_t)qq)) : 0.0;
-          double a = pv[0];
-#pragma unroll
-          for (int qq = 1; qq < kClMax; ++qq) a += pv[qq];
-          return rowc[(size_t)ii * (2 * KT + 2) + k] + a;
-        };
-        if (KT == 1) {
+        // the partials sit in the owners' shared memory: every load of an item is issued before the first add
+        if (by_class) {
+          if (chave && cc >= 1) lc = gather(crow, cc - 1);
+        } else if (KT == 1) {
           if (ct < nrows) l[0] = gather(ct, 0);
         } else {
+          // thread <-> (row, class) item first (one round of remote loads for all classes), then thread <-> row
           for (int item = ct; item < nrows * KT; item += kCT) {
             const int k = item / nrows, ii = item - k * nrows;
             dl[ii * KT + k] = gather(ii, k);
@@ -570,7 +590,9 @@ __global__ void __launch_bounds__(kFT, 1) k_traj(Geom g, Bufs b, FusedGeom fg, i
           dl[ii * KT + k] = t;
         }
         named_bar(kBarCompute, kCT);
-        if (ct < nrows) {
+        if (by_class) {
+          if (chave && cc >= 1) lc = rowc[(size_t)crow * (2 * KT + 2) + cc - 1] + dl[crow * KT + cc - 1];
+        } else if (ct < nrows) {
 #pragma unroll
           for (int k = 0; k < KT; ++k) l[k] = rowc[(size_t)ct * (2 * KT + 2) + k] + dl[ct * KT + k];
         }
@@ -578,13 +600,47 @@ __global__ void __launch_bounds__(kFT, 1) k_traj(Geom g, Bufs b, FusedGeom fg, i
       // next step's prior-gradient terms, by the warps that hold no row of the softmax below (needed only
       // after the second barrier)
       {
-        int base = (nrows + 31) & ~31;
+        int base = by_class ? 32 * ((nrows + RPW - 1) / RPW) : ((nrows + 31) & ~31);
         if (base >= kCT) base = 0;
         if (ct >= base)
           for (int e = ct - base; e < ncols; e += kCT - base) prior_gradient(e);
       }
       double ll = 0;
-      if (ct < nrows) {
+      if (by_class) {
+        if (w * RPW < nrows) {   // warp-uniform: all 32 lanes take part in the shuffles
+          // find_normlv (utils.cpp:10-26) with the same operations in the same order as the thread-per-row form:
+          // m = max(0, l_1..l_K); se = exp(0 - m) + exp(l_1 - m) + ... (left to right); lse = log(se) + m
+          const int rb = min(cr, RPW - 1) * LPR;   // first lane of this lane's row
+          double m = 0.0;
+#pragma unroll
+          for (int q = 0; q < LPR; ++q) m = fmax(m, __shfl_sync(0xffffffffu, lc, rb + q));
+          const double e = exp(lc - m);
+          double se = __shfl_sync(0xffffffffu, e, rb);
+#pragma unroll
+          for (int q = 1; q < LPR; ++q) se += __shfl_sync(0xffffffffu, e, rb + q);
+          const double lse = log(se) + m;
+          const double nl = lc - lse;
+          if (chave) {
+            const int i = row0 + crow;
+            const double* rc = rowc + (size_t)crow * (2 * KT + 2);
+            if ((int)rc[2 * KT] == cc) ll = nl;
+            if (cc >= 1) {
+              const int k = cc - 1;
+              const double res = exp(nl) - rc[KT + k];
+              if (last_step) b.lv[(int64_t)k * n_s + i] = lc;   // the proposal's linear predictor: only the final one is state
+              if (CL) {
+                // push the new residual into every block's copy
+                const uint32_t dst = smem_u32(Rs) + (uint32_t)(k * n_e + i) * 8u;
+#pragma unroll
+                for (int qq = 0; qq < kClMax; ++qq)
+                  if (qq < (int)G) st_dsmem(map_to_cta(dst, (uint32_t)qq), res);
+              } else {
+                __stcg(&b.R[(int64_t)k * n_s + i], res);
+              }
+            }
+          }
+        }
+      } else if (ct < nrows) {
         const int i = row0 + ct;
         const double* rc = rowc + (size_t)ct * (2 * KT + 2);
         const int row_yb = (int)rc[2 * KT];
