@@ -339,12 +339,17 @@ int enqueue_step(htlr_handle* h, int L, bool until_energy_only = false) {
   };
   launch_select(g, b, st); ++nk;
   launch_begin(g, b, st); ++nk;
-  {
-    ProfScope ps(h, 0);
-    launch_lv_sweep(g, b, 0, nullptr, nullptr, nullptr, st);
-    ++nk;
+  if (!h->fused) {
+    // the reference's DetachFixlv (gibbs.cpp:197-229) and the softmax before the first gradient; the fused
+    // trajectory kernels need neither: they carry lv and the residual across iterations and add only
+    // X[:, iup] (delta_new - delta_old) per step
+    {
+      ProfScope ps(h, 0);
+      launch_lv_sweep(g, b, 0, nullptr, nullptr, nullptr, st);
+      ++nk;
+    }
+    launch_softmax(g, b, 0, nullptr, nullptr, nullptr, nullptr, nullptr, st); ++nk;
   }
-  launch_softmax(g, b, 0, nullptr, nullptr, nullptr, nullptr, nullptr, st); ++nk;
   if (h->fused) {
     ProfScope ps(h, 0);
     h->fg.timing = h->fgc.timing = h->profiling ? 1 : 0;
@@ -430,7 +435,7 @@ cudaGraphExec_t get_graph(htlr_handle* h, int L, int reps = 1) {
 int kernels_per_step(const htlr_handle* h, int L) {
   int per_grad = h->sharded ? 3 : 2;
   int n = 2 + 2 + per_grad + L * (2 + per_grad) + 1 + 1 + 1 + 1;
-  if (h->fused) n = 2 + 2 + 1 + 1 + 1 + 1 + (h->cfg.algo == HTLR_ALGO_CLUSTER_ONLY ? 0 : 1) + (h->use_cluster ? 1 : 0) +
+  if (h->fused) n = 2 + 1 + 1 + 1 + 1 + (h->cfg.algo == HTLR_ALGO_CLUSTER_ONLY ? 0 : 1) + (h->use_cluster ? 1 : 0) +
                      (h->use_small ? 1 : 0);
   if (h->cfg.ptype == HTLR_PRIOR_T && h->cfg.eta > 1e-10) n += 1;
   if (h->cfg.ptype == HTLR_PRIOR_T && !(h->cfg.eta > 1e-10)) n -= 2;
@@ -546,7 +551,7 @@ void do_create(const htlr_cfg* cfg, const double* X, int64_t ldx, const double* 
     // everything create allocates, in one chunk (upper bound of the dalloc calls below + alignment slack)
     const size_t Hh = (size_t)c.iters_rmc + 1 + (c.keep_warmup_hist ? c.iters_h : 0);
     const size_t nkk = (size_t)g.n_s * K, nv = (size_t)nvar + 64;   // (+64: one more int array than doubles counted)
-    size_t dbl = (c.x_on_device ? 0 : (size_t)round_up(n, 16) * nv) + nkk + nv + nv * K + 2 * nv + 4 * nkk +
+    size_t dbl = (c.x_on_device ? 0 : (size_t)round_up(n, 16) * nv) + nkk + nv + nv * K + 2 * nv + 5 * nkk +
                  2 * nv * K + 3 * nv + nv * K + 1 + (size_t)g.g_rt * nv * K +
                  (size_t)std::max(g.lv_cs, g.sm_count) * K * g.n_s + Hh * (nv * (K + 2) + 4);
     size_t bytes = dbl * sizeof(double) + ((size_t)n + 3 * nv) * sizeof(int) + nv +
@@ -596,6 +601,7 @@ void do_create(const htlr_cfg* cfg, const double* X, int64_t ldx, const double* 
   b.lv = h->dalloc<double>(nk);
   b.lv_old = h->dalloc<double>(nk);
   b.lv_fix = h->dalloc<double>(nk);
+  b.R_old = h->dalloc<double>(nk);
   b.R = h->dalloc<double>(nk);
   b.iup = h->dalloc<int>(nvar);
   b.ifix = h->dalloc<int>(nvar);
@@ -1040,6 +1046,7 @@ int htlr_cuda_trajectory(htlr_handle* h, const double* momt, int32_t L, double* 
     // restore
     CU(cudaMemcpyAsync(h->b.ctl, h->t_ctlsave, sizeof(Ctl), cudaMemcpyDeviceToDevice, h->st));
     CU(cudaMemcpyAsync(h->b.lv, h->t_lvsave, nk * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+    CU(cudaMemcpyAsync(h->b.R, h->b.R_old, nk * sizeof(double), cudaMemcpyDeviceToDevice, h->st));   // k_begin's copy
     CU(cudaStreamSynchronize(h->st));
   });
 }

@@ -67,7 +67,7 @@ struct Bufs {
   const double* ddn;    // colsum(X^2)/4
   // chain state
   double *deltas, *sigmasbt, *var_deltas;   // nvar x K col-major, nvar, nvar
-  double *lv, *lv_old, *lv_fix, *R;         // [k][i], stride n_s (class columns 1..K; class 0 is 0)
+  double *lv, *lv_old, *lv_fix, *R, *R_old;  // [k][i], stride n_s (class columns 1..K; class 0 is 0)
   // restricted set + compact per-feature work arrays (index r = position in iup)
   int *iup, *ifix;
   int* posof;           // inverse map: position of feature j in iup, or -1 (written by k_select)

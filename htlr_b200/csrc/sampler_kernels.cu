@@ -147,6 +147,16 @@ __global__ void __launch_bounds__(256) k_begin(Geom g, Bufs b) {
       pb += m * m;
     }
   }
+  // CacheOldValues (gibbs.cpp:483-491) for the row-sized state: the linear predictor and the residual of the current
+  // point. The fused trajectory kernels carry both from iteration to iteration (no detach sweep, no softmax
+  // before the first gradient), so a rejected proposal must find them again.
+  {
+    const int64_t tot = (int64_t)K * g.n_s;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < tot; e += (int64_t)gridDim.x * blockDim.x) {
+      b.lv_old[e] = b.lv[e];
+      b.R_old[e] = b.R[e];
+    }
+  }
   pa = block_sum(pa, sm);
   pb = block_sum(pb, sm);
   if (threadIdx.x == 0) { b.red[blockIdx.x].a = pa; b.red[blockIdx.x].b = pb; }
@@ -542,7 +552,7 @@ __global__ void __launch_bounds__(256) k_commit(Geom g, Bufs b) {
     if (tid == 0) ctl->loglike = ctl->loglike_new;
   } else {
     const int64_t tot = (int64_t)K * g.n_s;
-    for (int64_t e = tid; e < tot; e += nt) b.lv[e] = b.lv_old[e];
+    for (int64_t e = tid; e < tot; e += nt) { b.lv[e] = b.lv_old[e]; b.R[e] = b.R_old[e]; }
   }
 }
 

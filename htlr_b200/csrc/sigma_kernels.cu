@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(256) k_tail_t(Geom g, Bufs b) {
   }
   if (!accept) {
     const int64_t tot = (int64_t)K * g.n_s;
-    for (int64_t e = tid; e < tot; e += nt) b.lv[e] = b.lv_old[e];
+    for (int64_t e = tid; e < tot; e += nt) { b.lv[e] = b.lv_old[e]; b.R[e] = b.R_old[e]; }
   }
   if (last_block(&ctl->ticket[3], gridDim.x)) {
     if (threadIdx.x == 0) {

@@ -9,8 +9,9 @@
 //   gradient phase  warp <-> 4 columns at a time: lane-strided dot products with the residual (128-bit
 //                   shared-memory loads), interleaved xor-shuffle trees;
 //   update phase    thread <-> column: DNlogpost / MoveMomt / UpdateMomtAndDeltas and the next prior-gradient term;
-//   lv phase        thread <-> (row, column chunk): lv = lv_fix + sum_j X[i, j] delta[j, :] over the chunk's columns
-//                   in ascending order, chunks summed in order, row softmax, residual; log-likelihood at the end.
+//   lv phase        thread <-> (row, column chunk): lv += sum_j X[i, j] (delta_new - delta_old)[j, :] over the chunk's
+//                   columns in ascending order, chunks summed in order (the predictor is carried from step to step,
+//                   like k_traj: no detached fixed part), row softmax, residual; log-likelihood at the end.
 // Launched ahead of the cluster-mode and grid-mode kernels; it decides on the device whether the restricted set
 // fits (then sets Ctl::traj_done so the others return at once) or leaves the proposal to them.
 #include <algorithm>
@@ -47,18 +48,18 @@ __global__ void __launch_bounds__(kST, 1) k_traj_small(Geom g, Bufs b, int L, in
   if (RPT > kRptMax || u > u_max) return;
   // ---- shared-memory layout (doubles)
   const size_t need = (size_t)u * n_e + (size_t)KT * n_e + (CH > 1 ? (size_t)KT * CH * n32 : 0) +
-                      (size_t)u * (4 * KT + 2) + (size_t)(u + 1) / 2 + 2 * NW + 8;
+                      (size_t)u * (5 * KT + 2) + (size_t)(u + 1) / 2 + 2 * NW + 8;
   if (need > (size_t)smem_doubles) return;       // does not fit: the cluster / grid kernels take the proposal
   extern __shared__ __align__(128) unsigned char sm_raw[];
   double* Xs = reinterpret_cast<double*>(sm_raw);            // [u][n_e]
   double* Rs = Xs + (size_t)u * n_e;                          // [KT][n_e]
   double* part = Rs + (size_t)KT * n_e;                       // [KT][CH][n32] (CH > 1)
-  double* st = part + (CH > 1 ? (size_t)KT * CH * n32 : 0);   // [u][3*KT+2]: d, m, prior gradient, sig, step
-  double* gsm = st + (size_t)u * (3 * KT + 2);                // [u][KT] gradient of the step
+  double* st = part + (CH > 1 ? (size_t)KT * CH * n32 : 0);   // [u][4*KT+2]: d, m, prior gradient, sig, step, increment of d
+  double* gsm = st + (size_t)u * (4 * KT + 2);                // [u][KT] gradient of the step
   double* red = gsm + (size_t)u * KT;                         // [2*NW]
   uint64_t* bar = reinterpret_cast<uint64_t*>(red + 2 * NW);  // one mbarrier
   int* cidx = reinterpret_cast<int*>(bar + 1);                // [u]
-  constexpr int CS = 3 * KT + 2;
+  constexpr int CS = 4 * KT + 2;
   const double Cd = (double)ctl->C;
 
   if (tid == 0) {
@@ -101,7 +102,7 @@ __global__ void __launch_bounds__(kST, 1) k_traj_small(Geom g, Bufs b, int L, in
   const int ch = CH > 1 ? tid / n32 : 0;
   const int row_first = CH > 1 ? tid - ch * n32 : tid;
   const bool owner = ch == 0;    // applies the softmax
-  double fixv[kRptMax][KT], yv[kRptMax][KT];
+  double fixv[kRptMax][KT], yv[kRptMax][KT];   // fixv: the row's running linear predictor
   int ybv[kRptMax];
 #pragma unroll
   for (int q = 0; q < kRptMax; ++q) {
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__(kST, 1) k_traj_small(Geom g, Bufs b, int L, in
     if (owner && i < n && (q == 0 || CH == 1)) {
       ybv[q] = b.ybase[i];
 #pragma unroll
-      for (int k = 0; k < KT; ++k) { fixv[q][k] = b.lv_fix[(int64_t)k * n_s + i]; yv[q][k] = b.ymat[(int64_t)k * n_s + i]; }
+      for (int k = 0; k < KT; ++k) { fixv[q][k] = b.lv[(int64_t)k * n_s + i]; yv[q][k] = b.ymat[(int64_t)k * n_s + i]; }
     }
   }
   // columns of this thread's chunk in the lv phase
@@ -195,7 +196,11 @@ __global__ void __launch_bounds__(kST, 1) k_traj_small(Geom g, Bufs b, int L, in
         for (int k = 1; k < KT; ++k) sd += dn[k];
         const double sdc = sd / Cd;
 #pragma unroll
-        for (int k = 0; k < KT; ++k) { sc[k] = dn[k]; sc[2 * KT + k] = (dn[k] - sdc) / sig; }
+        for (int k = 0; k < KT; ++k) {
+          sc[3 * KT + 2 + k] = __dsub_rn(dn[k], sc[k]);   // what the lv phase adds
+          sc[k] = dn[k];
+          sc[2 * KT + k] = (dn[k] - sdc) / sig;
+        }
       }
     }
     __syncthreads();
@@ -215,7 +220,7 @@ __global__ void __launch_bounds__(kST, 1) k_traj_small(Geom g, Bufs b, int L, in
       if (have_row) {
         for (int c = cl0; c < cl1; ++c) {
           const double x = Xs[(size_t)c * n_e + i];
-          const double* sc = st + (size_t)c * CS;
+          const double* sc = st + (size_t)c * CS + 3 * KT + 2;
 #pragma unroll
           for (int k = 0; k < KT; ++k) a[k] = fma(x, sc[k], a[k]);
         }
@@ -239,7 +244,7 @@ __global__ void __launch_bounds__(kST, 1) k_traj_small(Geom g, Bufs b, int L, in
         double l[KT];
         double m = 0.0;
 #pragma unroll
-        for (int k = 0; k < KT; ++k) { l[k] = fixv[q][k] + a[k]; m = fmax(m, l[k]); }
+        for (int k = 0; k < KT; ++k) { l[k] = fixv[q][k] + a[k]; fixv[q][k] = l[k]; m = fmax(m, l[k]); }
         double se = exp(0.0 - m);
 #pragma unroll
         for (int k = 0; k < KT; ++k) se += exp(l[k] - m);
@@ -249,8 +254,9 @@ __global__ void __launch_bounds__(kST, 1) k_traj_small(Geom g, Bufs b, int L, in
         for (int k = 0; k < KT; ++k) {
           const double nl = l[k] - lse;
           if (ybv[q] == k + 1) ll += nl;
-          Rs[k * n_e + i] = exp(nl) - yv[q][k];
-          if (last) b.lv[(int64_t)k * n_s + i] = l[k];
+          const double res = exp(nl) - yv[q][k];
+          Rs[k * n_e + i] = res;
+          if (last) { b.lv[(int64_t)k * n_s + i] = l[k]; b.R[(int64_t)k * n_s + i] = res; }
         }
       }
     }

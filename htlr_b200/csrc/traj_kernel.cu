@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(kFT, 1) k_traj(Geom g, Bufs b, FusedGeom fg, i
   double* redsm = lasm + (NG > 1 ? (size_t)KT * n_e : 0);                    // [kCW]
   double* dl = redsm + kCW;                                                  // [rpc*KT]
   double* wsum = dl + ((fg.rpc * KT + 1) & ~1);                              // [kCW][rpc*KT] per-warp sums of the partials (grid mode)
-  double* rowc = wsum + (CL ? 0 : (size_t)kCW * fg.rpc * KT);                // [rpc][2*KT+2] lv_fix, ymat, label
+  double* rowc = wsum + (CL ? 0 : (size_t)kCW * fg.rpc * KT);                // [rpc][2*KT+2] running lv, ymat, label
   double* cst = rowc + (size_t)fg.rpc * (2 * KT + 2);                        // [ncmax][CS]
   double* lp_own = cst + (((size_t)fg.ncmax * CS + 1) & ~(size_t)1);         // cluster mode: own lv partial [KT][n_e]
   double* Rs = lp_own + (CL ? (size_t)KT * n_e : 0);                         // cluster mode: residual copy [KT][n_e]
@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(kFT, 1) k_traj(Geom g, Bufs b, FusedGeom fg, i
     rc[2 * KT] = (double)b.ybase[row0 + ct];
 #pragma unroll
     for (int k = 0; k < KT; ++k) {
-      rc[k] = b.lv_fix[(int64_t)k * n_s + row0 + ct];
+      rc[k] = b.lv[(int64_t)k * n_s + row0 + ct];   // running linear predictor of the row (updated every step)
       rc[KT + k] = b.ymat[(int64_t)k * n_s + row0 + ct];
     }
   }
@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(kFT, 1) k_traj(Geom g, Bufs b, FusedGeom fg, i
       if (wg == pw) {
         if (lane < V) {
           const int c = lane / KT, k = lane - c * KT;
-          double dnew = 0.0;
+          double dnew = 0.0, dinc = 0.0;
           if (c < nc) {
             double gsum = gp[lane];
 #pragma unroll
@@ -420,21 +420,23 @@ __global__ void __launch_bounds__(kFT, 1) k_traj(Geom g, Bufs b, FusedGeom fg, i
             if (s < L) {
               mm = __dsub_rn(mm, kick);
               dnew = __dadd_rn(dk, __dmul_rn(stp, mm));
+              dinc = __dsub_rn(dnew, dk);
             }
             st[k] = dnew;
             st[KT + k] = mm;
           }
-          dnb[lane] = dnew;
+          dnb[lane] = dinc;
         }
       }
       if (GW > 1) named_bar(kBarGroup + grp, GT); else __syncwarp();
-      // ---- the tile's contribution to the next linear predictor, from the registers
+      // ---- the tile's contribution to the CHANGE of the linear predictor, from the registers: the predictor is
+      // carried from step to step (lv += X[:, iup] (delta_new - delta_old)), so no detached fixed part is needed
       if (s < L) {
 #pragma unroll
         for (int c = 0; c < TC; ++c) {
 #pragma unroll
           for (int k = 0; k < KT; ++k) {
-            const double dnk = dnb[c * KT + k];   // 0 for a column past the block's last one
+            const double dnk = dnb[c * KT + k];   // coefficient increment; 0 for a column past the block's last one
 #pragma unroll
             for (int m = 0; m < NRP; ++m) {
               la[m][0][k] = fma(x[c][m].x, dnk, la[m][0][k]);
@@ -622,12 +624,16 @@ __global__ void __launch_bounds__(kFT, 1) k_traj(Geom g, Bufs b, FusedGeom fg, i
           const double nl = lc - lse;
           if (chave) {
             const int i = row0 + crow;
-            const double* rc = rowc + (size_t)crow * (2 * KT + 2);
+            double* rc = rowc + (size_t)crow * (2 * KT + 2);
             if ((int)rc[2 * KT] == cc) ll = nl;
             if (cc >= 1) {
               const int k = cc - 1;
               const double res = exp(nl) - rc[KT + k];
-              if (last_step) b.lv[(int64_t)k * n_s + i] = lc;   // the proposal's linear predictor: only the final one is state
+              rc[k] = lc;                                       // the row's running linear predictor
+              if (last_step) {
+                b.lv[(int64_t)k * n_s + i] = lc;                // the proposal's lv and residual: only the final ones are state
+                if (CL) b.R[(int64_t)k * n_s + i] = res;
+              }
               if (CL) {
                 // push the new residual into every block's copy
                 const uint32_t dst = smem_u32(Rs) + (uint32_t)(k * n_e + i) * 8u;
@@ -642,7 +648,7 @@ __global__ void __launch_bounds__(kFT, 1) k_traj(Geom g, Bufs b, FusedGeom fg, i
         }
       } else if (ct < nrows) {
         const int i = row0 + ct;
-        const double* rc = rowc + (size_t)ct * (2 * KT + 2);
+        double* rc = rowc + (size_t)ct * (2 * KT + 2);
         const int row_yb = (int)rc[2 * KT];
         double m = 0.0;
 #pragma unroll
@@ -657,7 +663,11 @@ __global__ void __launch_bounds__(kFT, 1) k_traj(Geom g, Bufs b, FusedGeom fg, i
           const double nl = l[k] - lse;
           if (row_yb == k + 1) ll = nl;
           const double res = exp(nl) - rc[KT + k];
-          if (last_step) b.lv[(int64_t)k * n_s + i] = l[k];   // the proposal's linear predictor: only the final one is state
+          rc[k] = l[k];                                       // the row's running linear predictor
+          if (last_step) {
+            b.lv[(int64_t)k * n_s + i] = l[k];                // the proposal's lv and residual: only the final ones are state
+            if (CL) b.R[(int64_t)k * n_s + i] = res;
+          }
           if (CL) {
             // push the new residual into every block's copy
             const uint32_t dst = smem_u32(Rs) + (uint32_t)(k * n_e + i) * 8u;
