@@ -620,8 +620,10 @@ def main():
         nvar = p + 1
         m_detach = u if u <= nvar // 2 else nvar - u
         L = HTLR_DEFAULTS["leap_L"]
-        bytes_two = 8.0 * n * (m_detach + u + 2 * L * u)
-        bytes_min = 8.0 * n * (m_detach + (L + 1) * u)
+        bytes_two = 8.0 * n * (m_detach + u + 2 * L * u)     # the reference's algorithm
+        # what the fused kernels actually read: (L+1) sweeps of X[:, iup], no detach sweep (lv is carried from step to
+        # step); SURVEY 8d's B_iter,min = 8 n [m + (L+1) u] still counts the detach sweep
+        bytes_min = 8.0 * n * ((0 if a.algo != 1 else m_detach) + (L + 1) * u)
         it_s_1gpu = a.steps / (res["ms"] * 1e-3)
         line = {
             "metric": "mcmc_iterations_per_sec", "value": value, "unit": "it/s", "n_gpus": world, "steps": a.steps,
@@ -641,7 +643,7 @@ def main():
             "clocks": clk,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": (ach / peak) if ach else None, "traffic": ncu_traffic("sweep"),
-                         "kernel": "k_lv_sweep + k_grad_sweep (X sweeps)" if a.algo == 1 else "k_traj_fused (L+1 X sweeps per launch) + detach sweep", "peak_source": peak_src,
+                         "kernel": "k_lv_sweep + k_grad_sweep (X sweeps)" if a.algo == 1 else "k_traj (L+1 X sweeps per launch; no detach sweep: lv is carried across steps)", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": pr["sweep_bytes"] / max(pr["sweep_launches"], 1),
                          "launches_timed": pr["sweep_launches"], "frac_of_nominal_8TBs": (ach / 8000.0) if ach else None,
                          "fused_phase_ms_per_launch_block0": {k: pr[k] / max(res["prof_steps"], 1) for k in
