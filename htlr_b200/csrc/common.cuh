@@ -57,6 +57,9 @@ struct Ctl {
   unsigned long long tl_prev, tl_acc[12];
   // scratch counters for "last block finishes" reductions
   unsigned int ticket[8];
+  // k_select over several blocks: per-block counts chained through (epoch << 32 | count) words
+  unsigned long long sel_flag[32];
+  unsigned int sel_epoch;
 };
 
 // Start-of-kernel time stamp for the per-iteration timeline; the marked kernels of an iteration run one after

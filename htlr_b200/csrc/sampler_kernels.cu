@@ -59,19 +59,30 @@ __global__ void k_colsumsq(Geom g, const double* __restrict__ X, double* __restr
 }
 
 // ------------------------------------------------------------------------------------------------
-// Ordered compaction of the restricted set by ONE block of 32 warps: warp w owns the contiguous segment
-// [w*seg, (w+1)*seg) and walks it 32 features at a time (coalesced), so ascending order falls out of ballots:
-// pass 1 counts, an exclusive scan over the 32 warp totals gives each warp its output offset, pass 2 writes.
+// Ordered compaction of the restricted set. A block of 32 warps owns a contiguous segment of features, warp w the
+// contiguous sub-segment [j0, j1) which it walks 32 features at a time (coalesced), so ascending order falls out of
+// ballots: pass 1 counts, an exclusive scan over the 32 warp totals gives each warp its offset inside the block,
+// pass 2 writes. With several blocks (one per 4096 features: a single SM reading and writing 300+ KB was 12 us
+// of every iteration at p = 20000) the block totals are chained: block b publishes (epoch, count) and waits for
+// the words of blocks 0..b-1 - blocks are dispatched in index order, so the ones it waits for are running or done.
+constexpr int kSelMaxBlocks = 32;
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
 __global__ void __launch_bounds__(1024) k_select(Geom g, Bufs b) {
   Ctl* ctl = b.ctl;
   timeline_mark(ctl, 0);
   __shared__ int s_w[32];
-  __shared__ int s_total;
+  __shared__ int s_total, s_prefix;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const int nvar = g.nvar;
+  const int nvar = g.nvar, G = gridDim.x, blk = blockIdx.x;
   const double cut = ctl->init_all ? -1.0 : ctl->sgmsq_cut;
-  const int seg = (((nvar + 31) / 32) + 31) & ~31;            // features per warp, a multiple of 32
-  const int j0 = min(nvar, w * seg), j1 = min(nvar, j0 + seg);
+  const unsigned want = ctl->sel_epoch + 1u;                 // this launch's epoch (bumped by the last block to finish)
+  const int segB = ((nvar + G - 1) / G + 1023) & ~1023;     // features per block, a multiple of 32 * 32
+  const int seg = segB / 32;                                 // features per warp, a multiple of 32
+  const int j0 = min(nvar, blk * segB + w * seg), j1 = min(nvar, j0 + seg);
   int cnt = 0;
 #pragma unroll 16
   for (int j = j0 + lane; j - lane < j1; j += 32) {   // 16 loads in flight: two or three L2 round trips per segment
@@ -89,11 +100,28 @@ __global__ void __launch_bounds__(1024) k_select(Geom g, Bufs b) {
       if (lane >= o) iv += t;
     }
     s_w[lane] = iv - v;  // exclusive warp offsets
-    if (lane == 31) s_total = iv;
+    const int total = __shfl_sync(0xffffffffu, iv, 31);
+    if (lane == 0) {
+      s_total = total;
+      if (G > 1) {
+        const unsigned long long word = ((unsigned long long)want << 32) | (unsigned)total;
+        asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(&ctl->sel_flag[blk]), "l"(word) : "memory");
+      }
+    }
+    // selected features in the blocks before this one
+    int before = 0;
+    if (lane < blk) {
+      unsigned long long f;
+      do { f = ld_acquire_u64(&ctl->sel_flag[lane]); } while ((unsigned)(f >> 32) != want);
+      before = (int)(unsigned)f;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+    if (lane == 0) s_prefix = before;
   }
   __syncthreads();
-  int pu = s_w[w];       // next position in iup for this warp
-  int pf = j0 - pu;      // next position in ifix
+  int pu = s_prefix + s_w[w];   // next position in iup for this warp
+  int pf = j0 - pu;             // next position in ifix
 #pragma unroll 4
   for (int j = j0 + lane; j - lane < j1; j += 32) {
     const bool in = j < j1;
@@ -105,8 +133,8 @@ __global__ void __launch_bounds__(1024) k_select(Geom g, Bufs b) {
     pu += __popc(mu);
     pf += __popc(mf);
   }
-  if (tid == 0) {
-    const int u = s_total;
+  if (blk == G - 1 && tid == 0) {
+    const int u = s_prefix + s_total;
     ctl->u = u;
     ctl->nfix = nvar - u;
     if (!ctl->init_all) {
@@ -114,6 +142,9 @@ __global__ void __launch_bounds__(1024) k_select(Geom g, Bufs b) {
       // Traject's choice of logw (gibbs.cpp:394-408); L itself is chosen by the host
       ctl->logw = (ctl->i_mc < ctl->iters_h / 2.0) ? -10.0 : ctl->s;
     }
+  }
+  if (G > 1 && last_block(&ctl->ticket[5], G)) {
+    if (tid == 0) ctl->sel_epoch = want;   // every block has read its epoch and the words it waited for
   }
 }
 
@@ -691,7 +722,12 @@ void launch_trace_summary(const Geom& g, const Bufs& b, int first, int last, int
 void launch_colsumsq(const Geom& g, const double* X, double* ddn, cudaStream_t st) {
   k_colsumsq<<<g.sm_count * 4, 256, 0, st>>>(g, X, ddn);
 }
-void launch_select(const Geom& g, const Bufs& b, cudaStream_t st) { k_select<<<1, 1024, 0, st>>>(g, b); }
+void launch_select(const Geom& g, const Bufs& b, cudaStream_t st) {
+  // measured (tools/timeline.py): p = 20000, 5 blocks 8.2 us against 13 us with one; p = 5000, 2 blocks 6.9 us against
+  // 5.2 us with one (the chained hand-over costs ~2 us) - so one block up to 8192 features
+  const int blocks = g.nvar <= 8192 ? 1 : std::min(kSelMaxBlocks, (g.nvar + 4095) / 4096);
+  k_select<<<blocks, 1024, 0, st>>>(g, b);
+}
 void launch_begin(const Geom& g, const Bufs& b, cudaStream_t st) { k_begin<<<g.e_grid, 256, 0, st>>>(g, b); }
 
 void launch_lv_sweep(const Geom& g, const Bufs& b, int mode, const int* idx, const int* cnt,
