@@ -212,3 +212,24 @@ def test_device_resident_inputs_give_the_same_chain():
     dev.close()
     for k in ("mcdeltas", "mcsigmasbt", "mcloglike", "mcuvar", "mchmcrej"):
         assert np.array_equal(a[k], b[k]), k
+
+
+@pytest.mark.parametrize("p", [8191, 8192, 50000, 140000], ids=["one-block", "two-blocks", "13-blocks", "max-blocks"])
+def test_restricted_set_selection_over_many_features(p):
+    """WhichUpdate (gibbs.cpp:156-170) with p beyond one block's segment: k_select chains its block counts; the
+    restricted set (ascending, same members) and the chain must equal the oracle's."""
+    import htlr_b200
+    from oracle import oracle as O
+    args = problem(24, p, 2, seed=p % 97, iters_h=1, iters_rmc=2, leap_L=2, leap_L_h=2, hmc_sgmcut=0.05, init="zero")
+    st = streams(args, seed=3)
+    gpu = htlr_b200.Sampler(**args, rng_mode=htlr_b200.fit.RNG_INJECT)
+    ora = O.OracleFit(**args)
+    ora.initialize()
+    ora.set_inject(st["normals"], st["uniforms"], st["gammas"], None)
+    sg = gpu.run(3, **st)
+    ora.run(3)
+    so = ora.iter_stats()
+    assert np.array_equal(sg["uvar"], so["uvar"]) and p / 400 < sg["uvar"][-1] < p / 20    # about 1 % of the features
+    a, b = gpu.fetch(), ora.fetch()
+    assert relerr(a["mcdeltas"], b["mcdeltas"]) < 1e-8 and relerr(a["mcsigmasbt"], b["mcsigmasbt"]) < 1e-9
+    gpu.close()
