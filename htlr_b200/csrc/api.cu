@@ -213,6 +213,7 @@ struct htlr_handle {
   FusedGeom fgc{};
   bool use_cluster = false; // launch the cluster-mode flavour ahead of the grid-mode one
   bool use_small = false;   // launch the single-block kernel ahead of both
+  bool skip_grid = false;   // the cluster-mode kernel covers every possible restricted set: no grid-mode launch
   int smem_optin = 0;
   unsigned long long small_base = 0;
   unsigned long long tl_base[12] = {};
@@ -365,7 +366,7 @@ int enqueue_step(htlr_handle* h, int L, bool until_energy_only = false) {
       CU(launch_traj_fused(g, b, h->fgc, L, st));
       ++nk;
     }
-    if (h->cfg.algo != HTLR_ALGO_CLUSTER_ONLY) {
+    if (!h->skip_grid) {
       CU(launch_traj_fused(g, b, h->fg, L, st));
       ++nk;
     }
@@ -435,7 +436,7 @@ cudaGraphExec_t get_graph(htlr_handle* h, int L, int reps = 1) {
 int kernels_per_step(const htlr_handle* h, int L) {
   int per_grad = h->sharded ? 3 : 2;
   int n = 2 + 2 + per_grad + L * (2 + per_grad) + 1 + 1 + 1 + 1;
-  if (h->fused) n = 2 + 1 + 1 + 1 + 1 + (h->cfg.algo == HTLR_ALGO_CLUSTER_ONLY ? 0 : 1) + (h->use_cluster ? 1 : 0) +
+  if (h->fused) n = 2 + 1 + 1 + 1 + 1 + (h->skip_grid ? 0 : 1) + (h->use_cluster ? 1 : 0) +
                      (h->use_small ? 1 : 0);
   if (h->cfg.ptype == HTLR_PRIOR_T && h->cfg.eta > 1e-10) n += 1;
   if (h->cfg.ptype == HTLR_PRIOR_T && !(h->cfg.eta > 1e-10)) n -= 2;
@@ -641,6 +642,11 @@ void do_create(const htlr_cfg* cfg, const double* X, int64_t ldx, const double* 
     if ((c.algo == HTLR_ALGO_FUSED_CLUSTER || c.algo == HTLR_ALGO_CLUSTER_ONLY) && !h->has_cluster)
       FAIL(HTLR_E_ARG, "cluster-mode trajectory kernel not available on this device");
     h->use_cluster = h->fused && h->has_cluster;
+    // small problems (config A: 2001 features): even u = nvar stays below the cluster kernel's limit, so the grid-mode
+    // launch could only ever return at once (1.5 us per iteration)
+    h->skip_grid = c.algo == HTLR_ALGO_CLUSTER_ONLY ||
+                   (c.algo == HTLR_ALGO_AUTO && h->use_cluster && h->fgc.cl_umax >= nvar);
+    if (h->skip_grid) h->fgc.cl_only = 1;   // nothing follows the cluster kernel: exceeding its limit is an error
     h->smem_optin = dev.smem_optin;
     h->use_small = h->fused && small_applies(g) &&
                    (((c.algo == HTLR_ALGO_AUTO || c.algo == HTLR_ALGO_CLUSTER_ONLY) && g.n <= 256) ||
