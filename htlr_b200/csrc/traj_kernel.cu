@@ -158,8 +158,8 @@ __global__ void __launch_bounds__(kFT, 1) k_traj(Geom g, Bufs b, FusedGeom fg, i
   double* ring = reinterpret_cast<double*>(smem_raw);                       // [NG][SG][TC][n_e]
   double* gpart = ring + (size_t)NG * SG * TC * n_e;                         // [2][kCW][VP] per-warp gradient partials
   double* dnsm = gpart + 2 * kCW * VP;                                       // [2][NG][VP] new coefficients of a tile
-  double* lasm = dnsm + 2 * NG * VP;                                         // [KT][n_e] one group's lv partial in transit (NG > 1)
-  double* redsm = lasm + (NG > 1 ? (size_t)KT * n_e : 0);                    // [kCW]
+  double* lasm = dnsm + 2 * NG * VP;                                         // [NG-1][KT][n_e] lv partials of groups 1.. in transit
+  double* redsm = lasm + (size_t)(NG - 1) * KT * n_e;                        // [kCW]
   double* dl = redsm + kCW;                                                  // [rpc*KT]
   double* wsum = dl + ((fg.rpc * KT + 1) & ~1);                              // [kCW][rpc*KT] per-warp sums of the partials (grid mode)
   double* rowc = wsum + (CL ? 0 : (size_t)kCW * fg.rpc * KT);                // [rpc][2*KT+2] running lv, ymat, label
@@ -451,39 +451,79 @@ __global__ void __launch_bounds__(kFT, 1) k_traj(Geom g, Bufs b, FusedGeom fg, i
     if (timer) { const long long t = clk(); atomicAdd(&ctl->ph_cycles[0], (unsigned long long)(t - tk0)); tk0 = t; }
     if (s == L) break;
 
-    // ---- every group is done with the sweep: next step's prior-gradient terms, then this block's lv partial
-    named_bar(kBarCompute, kCT);
-    // groups 1.. hand their lv registers to group 0 one after the other through a one-group buffer (every group
-    // maps threads to rows the same way), group 0 adds them in group order
-    if (NG > 1) {
-#pragma unroll 1
-      for (int gg = 1; gg < NG; ++gg) {
-        if (ntiles <= gg) break;   // that group (and every later one) had no tile: nothing to add
-        if (grp == gg) {
+    // Cross-group reduction of the lv partial. With 4 or 16 groups (n <= 512) every group leaves its registers in a slot
+    // of its own and group 0 adds the slots in group order after ONE barrier (config A 156 -> 149, config B full
+    // 551 -> 535 us per iteration). With 2 groups (n = 513..1024, config C) the one-slot hand-over below is kept: it
+    // costs two more barriers per step, but the instantiation with the slot writes ahead of the barrier measured
+    // 4 % slower on config C (the hot loop's schedule changes), same box, same run.
+    if constexpr (NG > 2) {
+      // ---- groups 1.. (those that had a tile) leave their lv registers in their own slot; after ONE barrier of the
+      // block group 0 adds the slots in group order (every group maps threads to rows the same way)
+      if (NG > 1 && grp >= 1 && grp < ntiles) {
+        double* slot = lasm + (size_t)(grp - 1) * KT * n_e;
 #pragma unroll
-          for (int m = 0; m < NRP; ++m) {
-            if (rval[m]) {
+        for (int m = 0; m < NRP; ++m) {
+          if (rval[m]) {
 #pragma unroll
-              for (int k = 0; k < KT; ++k)
-                *reinterpret_cast<double2*>(lasm + (size_t)k * n_e + roff[m]) = make_double2(la[m][0][k], la[m][1][k]);
-            }
+            for (int k = 0; k < KT; ++k)
+              *reinterpret_cast<double2*>(slot + (size_t)k * n_e + roff[m]) = make_double2(la[m][0][k], la[m][1][k]);
           }
         }
-        named_bar(kBarCompute, kCT);
-        if (grp == 0) {
+      }
+      named_bar(kBarCompute, kCT);   // every group is done with the sweep
+      if (NG > 1 && grp == 0) {
+#pragma unroll 1
+        for (int gg = 1; gg < NG; ++gg) {
+          if (ntiles <= gg) break;   // that group (and every later one) had no tile: nothing to add
+          const double* slot = lasm + (size_t)(gg - 1) * KT * n_e;
 #pragma unroll
           for (int m = 0; m < NRP; ++m) {
             if (rval[m]) {
 #pragma unroll
               for (int k = 0; k < KT; ++k) {
-                const double2 t = *reinterpret_cast<const double2*>(lasm + (size_t)k * n_e + roff[m]);
+                const double2 t = *reinterpret_cast<const double2*>(slot + (size_t)k * n_e + roff[m]);
                 la[m][0][k] += t.x;
                 la[m][1][k] += t.y;
               }
             }
           }
         }
-        named_bar(kBarCompute, kCT);
+      }
+    } else {
+      // ---- every group is done with the sweep: next step's prior-gradient terms, then this block's lv partial
+      named_bar(kBarCompute, kCT);
+      // groups 1.. hand their lv registers to group 0 one after the other through a one-group buffer (every group
+      // maps threads to rows the same way), group 0 adds them in group order
+      if (NG > 1) {
+#pragma unroll 1
+        for (int gg = 1; gg < NG; ++gg) {
+          if (ntiles <= gg) break;   // that group (and every later one) had no tile: nothing to add
+          if (grp == gg) {
+#pragma unroll
+            for (int m = 0; m < NRP; ++m) {
+              if (rval[m]) {
+#pragma unroll
+                for (int k = 0; k < KT; ++k)
+                  *reinterpret_cast<double2*>(lasm + (size_t)k * n_e + roff[m]) = make_double2(la[m][0][k], la[m][1][k]);
+              }
+            }
+          }
+          named_bar(kBarCompute, kCT);
+          if (grp == 0) {
+#pragma unroll
+            for (int m = 0; m < NRP; ++m) {
+              if (rval[m]) {
+#pragma unroll
+                for (int k = 0; k < KT; ++k) {
+                  const double2 t = *reinterpret_cast<const double2*>(lasm + (size_t)k * n_e + roff[m]);
+                  la[m][0][k] += t.x;
+                  la[m][1][k] += t.y;
+                }
+              }
+            }
+          }
+          named_bar(kBarCompute, kCT);
+        }
       }
     }
     if (cta < gact && grp == 0) {
@@ -817,7 +857,7 @@ bool fused_plan(const Geom& g, int smem_optin_bytes, int cl, FusedGeom* out) {
   else ncmax = (g.nvar + G - 1) / G + 1;   // worst case: every feature in the restricted set
   const size_t other = (size_t)(2 * kCW * 8 + 2 * kCW * 8 + kCW + ((rpc * K + 1) & ~1) + rpc * (2 * K + 2) + 2 +
                                 (cl > 0 ? 0 : kCW * rpc * K)) * sizeof(double) +
-                       (ng > 1 ? (size_t)K * n_e * sizeof(double) : 0) +
+                       (size_t)(ng - 1) * K * n_e * sizeof(double) +
                        (size_t)ncmax * ((3 * K + 2) * sizeof(double) + sizeof(int)) +
                        (cl > 0 ? (size_t)2 * K * n_e * sizeof(double) : 0) + 2 * kNsMax * sizeof(uint64_t) + 256;
   const size_t tile_bytes = (size_t)TC * col_bytes;
