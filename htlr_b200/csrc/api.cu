@@ -556,7 +556,7 @@ void do_create(const htlr_cfg* cfg, const double* X, int64_t ldx, const double* 
                  2 * nv * K + 3 * nv + nv * K + 1 + (size_t)g.g_rt * nv * K +
                  (size_t)std::max(g.lv_cs, g.sm_count) * K * g.n_s + Hh * (nv * (K + 2) + 4);
     size_t bytes = dbl * sizeof(double) + ((size_t)n + 3 * nv) * sizeof(int) + nv +
-                   ((size_t)std::max(std::max(g.e_grid, (n + 255) / 256), g.sm_count) + c.iters_h + c.iters_rmc) * sizeof(Red4) +
+                   ((size_t)std::max(std::max(g.e_grid, (n + 255) / 256), g.sm_count) + g.e_grid + 8 + c.iters_h + c.iters_rmc) * sizeof(Red4) +
                    sizeof(Ctl) + 64 * 256;
     h->arena_reserve(bytes);
   }
@@ -654,6 +654,7 @@ void do_create(const htlr_cfg* cfg, const double* X, int64_t ldx, const double* 
   }
   b.lvpart = h->dalloc<double>((size_t)std::max(g.lv_cs, g.sm_count) * K * g.n_s);
   b.red = h->dalloc<Red4>((size_t)std::max(std::max(g.e_grid, (n + 255) / 256), g.sm_count));
+  b.red_begin = h->dalloc<Red4>((size_t)g.e_grid);
   b.ctl = h->dalloc<Ctl>(1);
 
   // ---- history

@@ -76,6 +76,7 @@ struct Bufs {
   double* gpart;        // [g_rt][nvar*K] partials when g_rt > 1
   double* lvpart;       // [lv_cs][K][n_s]
   Red4* red;            // per-block partial sums
+  Red4* red_begin;      // k_begin's per-block energy partials (.a, .b; [0].c = number of blocks), read by k_energy
   Ctl* ctl;
   // history
   double *mcdeltas, *mcsigmasbt, *mcvardeltas, *mclogw, *mcloglike, *mcuvar, *mchmcrej;

@@ -137,6 +137,8 @@ __global__ void __launch_bounds__(1024) k_select(Geom g, Bufs b) {
     const int u = s_prefix + s_total;
     ctl->u = u;
     ctl->nfix = nvar - u;
+    ctl->ticket[4] = 0;  // grid-barrier counter of the fused trajectory kernel
+    ctl->traj_done = 0;
     if (!ctl->init_all) {
       ctl->uvar_acc += u;
       // Traject's choice of logw (gibbs.cpp:394-408); L itself is chosen by the host
@@ -190,20 +192,13 @@ __global__ void __launch_bounds__(256) k_begin(Geom g, Bufs b) {
   }
   pa = block_sum(pa, sm);
   pb = block_sum(pb, sm);
-  if (threadIdx.x == 0) { b.red[blockIdx.x].a = pa; b.red[blockIdx.x].b = pb; }
-  if (last_block(&ctl->ticket[0], gridDim.x)) {
-    // the block partials, summed by the whole block (fixed order: thread-strided, then block_sum's tree)
-    double A = 0, B = 0;
-    for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) { A += b.red[i].a; B += b.red[i].b; }
-    A = block_sum(A, sm);
-    B = block_sum(B, sm);
-    if (threadIdx.x == 0) {
-      ctl->nenergy_old = ctl->loglike - A / 2 - B / 2;
-      ctl->loglike_old = ctl->loglike;
-      ctl->ticket[4] = 0;  // grid-barrier counter of the fused trajectory kernel
-      ctl->traj_done = 0;
-      timeline_mark_end(ctl, 11);
-    }
+  // The old energy (CompNegEnergy at the current point, gibbs.cpp:432-437) is only read by the Metropolis test:
+  // the block partials are left for k_energy's last block to add (same order as a reduction here would use), which
+  // saves this kernel a fence, a ticket and a second round of loads on every iteration.
+  if (threadIdx.x == 0) {
+    b.red_begin[blockIdx.x].a = pa;
+    b.red_begin[blockIdx.x].b = pb;
+    if (blockIdx.x == 0) { b.red_begin[0].c = (double)gridDim.x; timeline_mark_end(ctl, 11); }
   }
 }
 
@@ -548,7 +543,15 @@ __global__ void __launch_bounds__(256) k_energy(Geom g, Bufs b, int g_has_loglik
     A = block_sum(A, sm);
     B = block_sum(B, sm);
     F = block_sum(F, sm);
+    // k_begin's partials: the energy at the starting point
+    double A0 = 0, B0 = 0;
+    const unsigned nb0 = (unsigned)b.red_begin[0].c;
+    for (unsigned i = threadIdx.x; i < nb0; i += blockDim.x) { A0 += b.red_begin[i].a; B0 += b.red_begin[i].b; }
+    A0 = block_sum(A0, sm);
+    B0 = block_sum(B0, sm);
     if (threadIdx.x == 0) {
+      ctl->nenergy_old = ctl->loglike - A0 / 2 - B0 / 2;
+      ctl->loglike_old = ctl->loglike;
       if (g_has_loglike) ctl->loglike_new = b.g[(int64_t)g.nvar * K];
       const double ne = ctl->loglike_new - A / 2 - B / 2;
       ctl->nenergy_new = ne;
