@@ -620,7 +620,7 @@ void do_create(const htlr_cfg* cfg, const double* X, int64_t ldx, const double* 
     FusedGeom fgm{};
     const bool can = dev.coop && !h->sharded && fused_plan(g, dev.smem_optin, 0, &fgm);
     if ((c.algo == HTLR_ALGO_FUSED || c.algo == HTLR_ALGO_FUSED_CLUSTER || c.algo == HTLR_ALGO_CLUSTER_ONLY) && !can)
-      FAIL(HTLR_E_ARG, "fused trajectory not applicable (needs K <= 4, a column tile in shared memory, one GPU)");
+      FAIL(HTLR_E_ARG, "fused trajectory not applicable (needs K <= 8, a column tile in shared memory, one GPU)");
     h->fused = can && c.algo != HTLR_ALGO_TWO_SWEEP;
     h->fg = fgm;
     if (h->fused && c.algo != HTLR_ALGO_FUSED) {   // AUTO, FUSED_CLUSTER, CLUSTER_ONLY, FUSED_NO_SMALL, SMALL_FIRST

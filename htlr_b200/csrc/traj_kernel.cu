@@ -139,7 +139,7 @@ __device__ __forceinline__ long long clk() {
 
 template <int KT>
 struct TileCols {
-  static constexpr int v = KT <= 2 ? 4 : 2;   // (column, class) values per tile: at most 8
+  static constexpr int v = KT <= 2 ? 4 : (KT <= 4 ? 2 : 1);   // (column, class) values per tile: at most 8
 };
 
 template <int KT, int NRP, int GW, bool CL>
@@ -550,9 +550,9 @@ __global__ void __launch_bounds__(kFT, 1) k_traj(Geom g, Bufs b, FusedGeom fg, i
       // each). Rows of a warp: RPW = 32 / C; used when the block's row slice fits 16 warps that way.
       constexpr int LPR = KT + 1;
       constexpr int RPW = 32 / LPR;
-      // (only a cluster's slice of n > 1536 rows with K = 4 does not fit: the thread-per-row form below is compiled
-      // for that instantiation alone)
-      constexpr bool kMayNotFit = CL && KT == 4;
+      // (only a cluster's row slice with K >= 4 may not fit - n > 1536 at K = 4, n > 768 at K = 8: the thread-per-row
+      // form below is compiled for those instantiations alone)
+      constexpr bool kMayNotFit = CL && KT >= 4;
       // Measured on one box (tools/timeline.py, us per iteration): K = 3 (config B) 235 -> 223 default cut, 569 -> 555
       // full; K = 1 and K = 2 are slower this way (config A 163.6 -> 167.5, config C default 408 -> 419), so they
       // keep the thread-per-row form.
@@ -805,9 +805,9 @@ cudaError_t launch_gw(const Geom& g, const Bufs& b, const FusedGeom& fg, int L, 
 
 template <int KT, bool CL>
 cudaError_t launch_k(const Geom& g, const Bufs& b, const FusedGeom& fg, int L, cudaStream_t st) {
-  switch (fg.nrp) {
-    case 1: return launch_gw<KT, 1, CL>(g, b, fg, L, st);
-    case 2: return launch_gw<KT, 2, CL>(g, b, fg, L, st);
+  if (fg.nrp == 1) return launch_gw<KT, 1, CL>(g, b, fg, L, st);
+  if constexpr (KT <= 4) {   // two row pairs per thread only fit the register file up to K = 4
+    if (fg.nrp == 2) return launch_gw<KT, 2, CL>(g, b, fg, L, st);
   }
   return cudaErrorInvalidValue;
 }
@@ -819,6 +819,10 @@ cudaError_t launch_mode(const Geom& g, const Bufs& b, const FusedGeom& fg, int L
     case 2: return launch_k<2, CL>(g, b, fg, L, st);
     case 3: return launch_k<3, CL>(g, b, fg, L, st);
     case 4: return launch_k<4, CL>(g, b, fg, L, st);
+    case 5: return launch_k<5, CL>(g, b, fg, L, st);
+    case 6: return launch_k<6, CL>(g, b, fg, L, st);
+    case 7: return launch_k<7, CL>(g, b, fg, L, st);
+    case 8: return launch_k<8, CL>(g, b, fg, L, st);
   }
   return cudaErrorInvalidValue;
 }
@@ -826,11 +830,11 @@ cudaError_t launch_mode(const Geom& g, const Bufs& b, const FusedGeom& fg, int L
 }  // namespace
 
 // Picks the group width and ring depth for (n, K); returns false when the fused path does not apply (a column
-// must fit in shared memory with room for a pipeline, K <= 4). cl = 0: grid mode (one block per SM); cl > 0:
+// must fit in shared memory with room for a pipeline, K <= 8). cl = 0: grid mode (one block per SM); cl > 0:
 // one cluster of cl blocks, which keeps per-column state for at most cl * ncmax restricted columns.
 bool fused_plan(const Geom& g, int smem_optin_bytes, int cl, FusedGeom* out) {
   const int n = g.n, K = g.K;
-  if (K < 1 || K > 4) return false;
+  if (K < 1 || K > 8) return false;
   const int npairs = (n + 1) / 2, n_e = 2 * npairs;
   if (npairs > kCT * kNlpMax) return false;
   const int G = cl > 0 ? cl : g.sm_count;
@@ -839,8 +843,9 @@ bool fused_plan(const Geom& g, int smem_optin_bytes, int cl, FusedGeom* out) {
   if (rpc > kCT) return false;
   if (G > 32 * kPartSlots) return false;   // row phase: one lane sums at most kPartSlots block partials
   // smallest group whose threads keep their row pairs (x, residual, lv partial) in registers
-  const int nrp_max = 2;   // row pairs per thread: x (TC x NRP double2), residual and lv partial stay in registers
-  const int TC = K <= 2 ? 4 : 2;   // TileCols<K>
+  // row pairs per thread: x (TC x NRP double2), residual and lv partial (4 NRP K doubles) stay in registers
+  const int nrp_max = K <= 4 ? 2 : 1;
+  const int TC = K <= 2 ? 4 : (K <= 4 ? 2 : 1);   // TileCols<K>
   int gw = 0;
   const char* force = std::getenv("HTLR_FUSED_GW");   // experiments only
   for (int cand : {1, 4, 8, 16}) {

@@ -52,7 +52,7 @@ enum { HTLR_RNG_DEVICE = 0, HTLR_RNG_INJECT = 1 };
  *            and the column's lv contribution from one staged copy of the column). The fused kernels carry the
  *            linear predictor and the residual from step to step and from iteration to iteration, so they need
  *            no DetachFixlv sweep (gibbs.cpp:197-229) and no softmax before the first gradient. Needs a column to
- *            fit in shared memory (n <= 2048, K <= 4, one GPU); AUTO picks it whenever it applies.
+ *            fit in shared memory (n <= 2048 for K <= 4, n <= 1024 for K = 5..8; one GPU); AUTO picks it whenever it applies.
  * FUSED_CLUSTER: the same kernel run by ONE thread-block cluster that exchanges partial sums through
  *            distributed shared memory and synchronises with hardware cluster barriers: lowest latency per
  *            leapfrog step, for restricted sets of a few hundred columns (falls back to FUSED by itself when

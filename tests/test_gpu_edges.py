@@ -48,9 +48,10 @@ def test_only_the_intercept_is_updated(algo):
     assert (out["mcuvar"][1:] == 1).all()
 
 
-@pytest.mark.parametrize("K1", [6, 9, 17])
-def test_many_classes_use_the_generic_kernels(K1):
-    """K = C - 1 > 4: no fused kernel, the two-sweep path with runtime K (up to 16)."""
+@pytest.mark.parametrize("K1", [6, 9, 10, 17, 18])
+def test_many_classes(K1):
+    """K = C - 1 up to 8: the fused kernel (one row pair per thread); K = 9..16: the two-sweep path with runtime K;
+    beyond: refused."""
     import htlr_b200
     args = problem(140, 30, K1, seed=K1, iters_rmc=3, iters_h=2, leap_L=4)
     if K1 - 1 > 16:

@@ -57,7 +57,10 @@ ALGOS = [pytest.param(1, id="two-sweep"), pytest.param(2, id="fused"), pytest.pa
 @pytest.mark.parametrize("algo", ALGOS)
 @pytest.mark.parametrize("n,p,C,L,cut", [(62, 200, 2, 5, 0.05), (300, 100, 3, 50, 0.05), (120, 80, 4, 20, 0.0),
                                           (1000, 60, 3, 10, 0.05), (90, 400, 2, 30, 1e-3), (37, 900, 5, 7, 0.0),
-                                          (1999, 50, 2, 6, 0.0), (501, 3000, 3, 4, 0.0)])
+                                          (1999, 50, 2, 6, 0.0), (501, 3000, 3, 4, 0.0),
+                                          # K = 5..8: fused kernel with one row pair per thread, one column per tile
+                                          (200, 80, 6, 10, 0.0), (1024, 40, 9, 6, 0.0), (513, 50, 8, 5, 0.05),
+                                          (61, 300, 7, 20, 0.05)])
 def test_trajectory_matches_oracle(n, p, C, L, cut, algo):
     """A whole leapfrog trajectory with injected identical momenta (north_star level-1 gate)."""
     args = problem(n, p, C, seed=7 * n + p, hmc_sgmcut=cut, scale=0.3)
@@ -91,6 +94,8 @@ def test_trajectory_matches_oracle(n, p, C, L, cut, algo):
     dict(n=70, p=90, C=3, thin=1, keep_warmup_hist=False, leap_step=0.9),   # plenty of rejections
     dict(n=64, p=70, C=2, thin=1, keep_warmup_hist=True, eta=0.5),           # logw ARS
     dict(n=66, p=50, C=3, thin=1, keep_warmup_hist=True, eta=0.005, s=-8.0), # 1e-10 < eta < 0.01: logw = s (gibbs.cpp:337-340)
+    dict(n=90, p=60, C=7, thin=1, keep_warmup_hist=True),                     # K = 6: fused kernel, K > 4 flavour
+    dict(n=600, p=40, C=9, thin=1, keep_warmup_hist=False, hmc_sgmcut=0.0),   # K = 8, every feature updated
 ])
 @pytest.mark.parametrize("algo", ALGOS)
 @pytest.mark.parametrize("use_graph", [False, True])
@@ -252,9 +257,10 @@ def test_fused_and_two_sweep_chains_agree():
 
 def test_fused_rejected_when_not_applicable():
     import htlr_b200
-    args = problem(60, 40, 7, seed=3)   # K = 6 > 4
-    with pytest.raises(htlr_b200.HtlrCudaError, match="fused trajectory not applicable"):
-        htlr_b200.Sampler(**args, algo=2)
-    s = htlr_b200.Sampler(**args, algo=0)   # AUTO falls back to the two-sweep path
-    s.run(2)
-    s.close()
+    for n, C in ((60, 11), (1100, 7)):   # K = 10 > 8; K = 6 with n > 1024 (one row pair per thread is the limit there)
+        args = problem(n, 40, C, seed=3)
+        with pytest.raises(htlr_b200.HtlrCudaError, match="fused trajectory not applicable"):
+            htlr_b200.Sampler(**args, algo=2)
+        s = htlr_b200.Sampler(**args, algo=0)   # AUTO falls back to the two-sweep path
+        s.run(2)
+        s.close()
