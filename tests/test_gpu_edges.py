@@ -234,3 +234,30 @@ def test_restricted_set_selection_over_many_features(p):
     a, b = gpu.fetch(), ora.fetch()
     assert relerr(a["mcdeltas"], b["mcdeltas"]) < 1e-8 and relerr(a["mcsigmasbt"], b["mcsigmasbt"]) < 1e-9
     gpu.close()
+
+
+@pytest.mark.parametrize("algo", [pytest.param(0, id="auto"), pytest.param(2, id="fused"), pytest.param(3, id="cluster"),
+                                  pytest.param(6, id="small-first"), pytest.param(1, id="two-sweep")])
+@pytest.mark.parametrize("shape", [(62, 400, 2, 0.05, 0.7), (300, 250, 4, 0.0, 0.1), (700, 150, 7, 0.05, 0.7)],
+                         ids=["n62-K1", "n300-K3-full", "n700-K6"])
+def test_linear_predictor_stays_consistent_with_the_coefficients(shape, algo):
+    """The fused kernels never rebuild lv = X delta: they carry it from step to step and from iteration to iteration
+    (as the reference's own lv_ drifts). After many accepted and rejected proposals the carried lv,
+    the log-likelihood and the coefficients must still describe the same point."""
+    import htlr_b200
+    n, p, C, cut, step = shape
+    args = problem(n, p, C, seed=n, iters_h=50, iters_rmc=350, leap_L=12, leap_L_h=4, hmc_sgmcut=cut, init="zero",
+                   leap_step=step)   # step sizes with plenty of rejections
+    s = htlr_b200.Sampler(**args, seed=5, algo=algo)
+    st = s.run(400)
+    state = s.state()
+    s.close()
+    assert 0.02 < st["rej"].mean() < 0.98                       # both branches exercised
+    X, K = np.asarray(args["X"]), C - 1
+    lv_ref = np.zeros((n, C))
+    lv_ref[:, 1:] = X @ state["deltas"]
+    assert relerr(state["lv"], lv_ref) < 1e-11
+    m = lv_ref.max(axis=1, keepdims=True)
+    lse = np.log(np.exp(lv_ref - m).sum(axis=1)) + m[:, 0]
+    ll_ref = float((lv_ref[np.arange(n), np.asarray(args["ybase"], dtype=int)] - lse).sum())
+    assert abs(state["loglike"] - ll_ref) < 1e-10 * abs(ll_ref)
