@@ -356,8 +356,10 @@ int enqueue_step(htlr_handle* h, int L, bool until_energy_only = false) {
     h->fg.timing = h->fgc.timing = h->profiling ? 1 : 0;
     if (h->use_small) {
       // a restricted set that fits in one SM's shared memory: no inter-block exchange at all
-      // measured (tools/small_sweep.py): it beats the cluster kernel while u * n <= ~6000 for n <= 256
-      CU(launch_traj_small(g, b, L, h->smem_optin, h->cfg.algo == HTLR_ALGO_SMALL_FIRST ? (1 << 20) : 6000 / g.n, st));
+      // measured (tools/small_sweep.py, after the cluster kernel's row phase was shortened): it beats the cluster
+      // kernel up to u ~ 96 at n = 62 and u ~ 10 at n = 200 - one SM's FP64 rate bounds the softmax of the rows
+      CU(launch_traj_small(g, b, L, h->smem_optin,
+                           h->cfg.algo == HTLR_ALGO_SMALL_FIRST ? (1 << 20) : std::max(4, 370000 / (g.n * g.n)), st));
       ++nk;
     }
     if (h->use_cluster) {

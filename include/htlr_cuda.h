@@ -60,7 +60,7 @@ enum { HTLR_RNG_DEVICE = 0, HTLR_RNG_INJECT = 1 };
  *            restricted set (cluster up to ~1.5 MB of X[:, iup]).
  * Ahead of both, AUTO and CLUSTER_ONLY launch a single-block kernel that runs the trajectory
  * entirely inside one SM (two __syncthreads per leapfrog step) whenever X[:, iup] fits in its shared memory
- * and it is the faster choice (measured: n <= 256 and u * n <= 6000, e.g. the first iterations of config A);
+ * and it is the faster choice (measured: n <= 256 and u <= 370000 / n^2, e.g. the first iterations of config A);
  * FUSED_NO_SMALL is AUTO without it, SMALL_FIRST uses it whenever it fits (tests).
  * CLUSTER_ONLY: FUSED_CLUSTER without the all-SM fallback launch, so that several chains (handles) can run
  *            concurrently on one GPU, each on its own 16-SM cluster (config D: 4 chains / folds per GPU). A
