@@ -7,8 +7,11 @@
 // contribution to the next linear predictor need only column j plus the n x K residual. So while a
 // column sits in shared memory (and, within a thread, in registers) its owners compute g_j = X_j' r, apply
 // the two half kicks as two separate subtractions (bit-compatible with the reference), drift delta_j, and
-// accumulate X_j delta_j into their private lv partial. Algorithmic X traffic per iteration:
-// 8 n (L+1) u bytes (+ detach).
+// accumulate X_j (delta_j,new - delta_j,old) into their private partial of the CHANGE of lv: the predictor itself is
+// carried from step to step by the row owners, and lv / the residual of the current point are kept across
+// iterations (k_begin saves them, a rejection restores them), so there is no DetachFixlv sweep
+// (gibbs.cpp:197-229) and no softmax before the first gradient. Algorithmic X traffic per iteration:
+// 8 n (L+1) u bytes.
 //
 // Structure: 16 warps per block (4 per SM sub-partition, so a thread may use 128 registers), organised as
 // NG = 16/GW independent GROUPS of GW warps. A group owns whole columns (round robin over the block's
@@ -23,12 +26,13 @@
 //     rows a thread needs live in registers for the sweep. Per column: dot products -> xor-shuffle tree ->
 //     (GW > 1) per-warp partials through shared memory and one named barrier of the group -> every thread
 //     forms the same gradient, prior gradient, MoveMomt / UpdateMomtAndDeltas (un-fused products) ->
-//     X_j delta_j accumulates into the thread's lv registers.
+//     X_j (delta_new - delta_old) accumulates into the thread's lv registers.
 //   Groups never wait for each other inside a sweep, so up to NG columns are in flight per SM; GW is the
 //   smallest group that keeps a thread's row pairs in registers.
 // After each sweep the group partials are summed in shared memory, the per-block lv partials are summed in
-// block order (deterministic), rows are soft-maxed and the new residual is published: two grid-wide barriers
-// per leapfrog step.
+// block order (deterministic) and added to the rows' running lv, rows are soft-maxed (K >= 3: one lane per class)
+// and the new residual is published: two grid-wide barriers per leapfrog step. The log-likelihood is reduced once,
+// after the last step.
 //
 // Two flavours (template flag CL):
 //   grid mode    — one block per SM, cooperative launch; partials and residual travel through L2 and the two
