@@ -7,7 +7,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhtlr_cuda.so")
+# HTLR_CUDA_LIB: another build of the same ABI (same-box A/B runs of two kernel versions: tools/ab/)
+LIB_PATH = os.environ.get("HTLR_CUDA_LIB") or os.path.join(_HERE, "libhtlr_cuda.so")
 
 c_dp = ctypes.POINTER(ctypes.c_double)
 c_ip = ctypes.POINTER(ctypes.c_int32)
