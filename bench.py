@@ -14,8 +14,18 @@ variance update, trace recording. Workloads (BASELINE.json configs):
              and reported in the "default_cut" block of the same line, with its own CPU baseline.
   B / D      gendata_MLR n=500 p=5000 C=4 / n=200 p=50000 C=2 (one chain).
 
-N > 1 (torchrun): independent chains, one per GPU, no communication (SURVEY 8e "replicas"); value is
-the sum over ranks. Prints ONE JSON line on rank 0.
+N > 1 (torchrun): the headline `value` is independent chains of the default workload, one per GPU, no communication
+(SURVEY 8e "replicas"), summed over ranks. The same line carries three more blocks, measured inside the same process
+group after the replica measurement (each with its own clock record):
+
+  sharded_parity  a small chain row-sharded over all N ranks (NCCL all-reduce of the gradient partials in every
+                  leapfrog step) against the same chain on rank 0 alone: identical accept history and restricted-set
+                  sizes, coefficients to 1e-10
+  E_row_sharded   config E at full size (n = 200000, p = 10000, C = 5), rows sharded over the N ranks: the strong-
+                  scaling point for this N (at N = 1 the single-GPU value, so the curve has an origin)
+  D_chains        config D: 4 chains per GPU running concurrently, no communication
+
+Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -49,11 +59,12 @@ WORKLOADS = {
               desc="colon (n=62, p=2000, binary), t prior df=1, leap=50, htlr() defaults (cut=0.05)"),
     "tiny": dict(gen="mlr", n=120, p=400, C=3, cut=0.0, seed=5, desc="tiny smoke workload"),
     # config E: ONE chain over all ranks, X row-sharded, NCCL all-reduce of the u x K gradient per leapfrog step
-    "E": dict(gen="mlr_device", n=200000, p=10000, C=5, cut=0.0, seed=1005,
+    "E": dict(gen="mlr_device", n=200000, p=10000, C=5, cut=0.0, seed=1005, leap_step=0.02,
               desc="tall gendata_MLR n=200000 p=10000 C=5 generated on device, t prior df=1, leap=50, cut=0, "
-                   "row-sharded over the ranks with an NCCL all-reduce of the gradient partials"),
+                   "leap.stepsize=0.02, row-sharded over the ranks with an NCCL all-reduce of the gradient partials"),
 }
 E_CPU_ROWS = 2000   # rows of the CPU-reference sample of workload E (rate scaled by E_CPU_ROWS / n)
+CHAIN_WARM_FULL = 60   # untimed iterations ahead of the warm-up steps in the full regime (the chain starts at zero)
 HTLR_DEFAULTS = dict(ptype="t", alpha=1.0, s=-10.0, eta=0.0, thin=1, leap_L=50, leap_L_h=5, leap_step=0.3,
                      keep_warmup_hist=False, silence=1, legacy=False)
 
@@ -154,6 +165,12 @@ def ncu_traffic(kernel_key):
         return None
 
 
+def workload_config(wl):
+    """The `config` object of a line: what is measured, nothing about how a run went - both arms print the same one."""
+    w = WORKLOADS[wl]
+    return {"workload": w["desc"], "regime": "full" if w["cut"] <= 0 else "restricted"}
+
+
 # ---------------------------------------------------------------------------------------------------
 def cpu_reference_rate(wl, max_iters, budget_s, warm_iters):
     """The reference's CPU sampler on this box's host cores, single thread (its hot loops are
@@ -225,7 +242,7 @@ def run_reference_arm(a):
     line = {"impl": "reference", "metric": "mcmc_iterations_per_sec", "value": rate, "unit": "it/s",
             "n_gpus": a.gpus, "steps": m, "warmup": a.warmup, "chain_warmup_iterations": warm, "ms_per_step": 1e3 / rate, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": w["desc"], "regime": "full" if w["cut"] <= 0 else "restricted"},
+            "config": workload_config(a.workload),
             "cpu_baseline": {"value": rate, "unit": "it/s", "cores": 1, "kind": kind,
                              "sample": f"{m} sampling iterations (L=50) of the same workload, time-boxed to ~150 s; "
                                        f"single thread of {cores} host cores (the reference's hot loops are single-threaded)"
@@ -268,8 +285,8 @@ def measure_workload(torch, wl, steps, warmup, device, chain_seed, dist, want_pr
     import htlr_b200
     w = WORKLOADS[wl]
     args = make_problem(wl, chain_seed)
-    warm_iters = 0 if w["cut"] <= 0 else 150   # restricted regime: let the restricted set settle first
-    total = warm_iters + warmup + steps
+    warm_iters = CHAIN_WARM_FULL if w["cut"] <= 0 else 150   # let the chain (and the restricted set) settle first:
+    total = warm_iters + warmup + steps                      # from a zero state the first proposals are all rejected
     prof_steps = min(steps, 20) if want_profile else 0
     smp = htlr_b200.Sampler(**dict(args, iters_h=warm_iters, iters_rmc=total + prof_steps), device=device,
                             seed=1000 + chain_seed, algo=ALGO)
@@ -288,10 +305,12 @@ def measure_workload(torch, wl, steps, warmup, device, chain_seed, dist, want_pr
         res["prof_steps"] = prof_steps
         smp.profile_enable(False)
     out = smp.fetch()
-    lo = max(warmup, 3) + 1   # trace slot of the first timed iteration (slot 0 is the initial state)
+    lo = max(warmup, 3) + 1   # trace slot of the first timed iteration (slot 0 is the initial state; warm-up
+                              # iterations are not recorded)
     res["uvar"] = float(np.mean(out["mcuvar"][lo:lo + steps]))
     res["rej"] = float(np.mean(out["mchmcrej"][lo:lo + steps]))
     res["n"], res["p"], res["K"] = args["n"], args["p"], args["K"]
+    res["chain_warm"] = warm_iters
     smp.close()
     return res
 
@@ -305,7 +324,7 @@ def measure_e2e(torch, wl, steps, device, chain_seed, dist):
     args["X"] = Xp.numpy().T
     w = WORKLOADS[wl]
     warm_iters = 0 if w["cut"] <= 0 else 150
-    a = dict(args, iters_h=warm_iters, iters_rmc=steps)
+    a = dict(args, iters_h=warm_iters, iters_rmc=steps)   # (a whole call: the chain starts from the zero state)
     times = []
     for rep in range(3):   # median of three whole calls (each: create + H2D, iterations, D2H of the trace, destroy)
         if dist is not None:
@@ -325,33 +344,34 @@ def measure_e2e(torch, wl, steps, device, chain_seed, dist):
     return (t1 - t0), h2d / steps, d2h / steps, warm_iters
 
 
-def measure_chains(torch, a, dist, rank, world, local):
-    """Config D: independent chains, `--chains-per-gpu` of them per GPU running CONCURRENTLY (each handle has its
-    own stream; CLUSTER_ONLY keeps every chain's trajectory on one 16-SM cluster so they overlap), no
-    communication. Also times the same chains one after the other for the concurrency gain."""
+def measure_chains(torch, steps, warmup, nch, dist, rank, world, local, cpu_baseline=True):
+    """Config D: independent chains, `nch` of them per GPU running CONCURRENTLY (each handle has its own stream;
+    CLUSTER_ONLY keeps every chain's trajectory on one 16-SM cluster so they overlap), no communication. Also times the
+    same chains one after the other for the concurrency gain. Returns the result dict on rank 0, None elsewhere."""
     import htlr_b200
     w = WORKLOADS["D"]
-    nch = a.chains_per_gpu
     warm_iters = 150
-    total = warm_iters + a.warmup + 2 * a.steps
+    total = warm_iters + warmup + 2 * steps
     smps = []
     for c in range(nch):
         args = make_problem("D", chain_seed=rank * nch + c)
         smps.append(htlr_b200.Sampler(**dict(args, iters_h=warm_iters, iters_rmc=total - warm_iters), device=local,
                                       seed=5000 + rank * nch + c, algo=4))
     for s in smps:
-        s.run(warm_iters + a.warmup)
+        s.run(warm_iters + warmup)
     streams = [torch.cuda.ExternalStream(s.stream) for s in smps]
     ev = lambda: torch.cuda.Event(enable_timing=True)
     # one after the other
     seq_ms = 0.0
     for s, st in zip(smps, streams):
         e0, e1 = ev(), ev()
-        s.sync(); e0.record(st); s.run_async(a.steps); e1.record(st); s.sync()
+        s.sync(); e0.record(st); s.run_async(steps); e1.record(st); s.sync()
         seq_ms += e0.elapsed_time(e1)
     # together
     for s in smps:
         s.sync()
+    clocks = ClockSampler(local)
+    clocks.start()
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
@@ -359,45 +379,48 @@ def measure_chains(torch, a, dist, rank, world, local):
     e0 = ev(); e0.record(streams[0])
     ends = []
     for s, st in zip(smps, streams):
-        s.run_async(a.steps)
+        s.run_async(steps)
         e1 = ev(); e1.record(st); ends.append(e1)
     for s in smps:
         s.sync()
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
+    clk = clocks.stop()
     ms = max(e0.elapsed_time(e) for e in ends)
     launches = sum(s.launch_count for s in smps) - l0
-    uvar = []
+    uvar, rej = [], []
     for s in smps:
         o = s.fetch()
-        uvar.append(float(np.mean(o["mcuvar"][-a.steps:])))
+        uvar.append(float(np.mean(o["mcuvar"][-steps:])))
+        rej.append(float(np.mean(o["mchmcrej"][-steps:])))
         s.close()
     t = torch.tensor([ms, seq_ms], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank != 0:
-        return
+        return None
     ms_max, seq_max = float(t[0]), float(t[1])
-    line = {"metric": "mcmc_iterations_per_sec", "value": world * nch * a.steps / (ms_max * 1e-3), "unit": "it/s",
-            "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_max / a.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": w["desc"], "regime": "restricted", "chains_per_gpu": nch, "chains_total": world * nch,
-                       "l2": "X[:, iup] of every chain is L2 / shared-memory resident (stated; latency-bound regime)",
-                       "parallelism": f"{nch} chains per GPU on separate streams, {world} GPU(s), no communication",
-                       "algorithm": "cluster-mode fused trajectory kernel (one 16-CTA cluster per chain)",
-                       "mean_nuvar": float(np.mean(uvar))},
-            "one_after_the_other": {"value": world * nch * a.steps / (seq_max * 1e-3), "unit": "it/s",
-                                    "concurrency_gain": seq_max / ms_max},
-            "e2e": None, "e2e_note": "measured on the default workload", "gpu_launches": launches,
-            "roofline": None, "roofline_note": "latency-bound regime (X[:, iup] of a chain is a few MB, L2 / shared-memory "
-                                               "resident); the HBM roofline is reported on the default workload"}
-    if not a.no_cpu_baseline:
-        rate, kind, m = cpu_reference_rate("D", 40, budget_s=25.0, warm_iters=150)
-        line["cpu_baseline"] = {"value": rate, "unit": "it/s", "cores": 1, "kind": kind,
-                                "sample": f"one chain, {m} sampling iterations after 150 warm-up iterations, 1 of "
-                                          f"{os.cpu_count()} host cores"}
-    print(json.dumps(line))
+    out = {"metric": "mcmc_iterations_per_sec", "value": world * nch * steps / (ms_max * 1e-3), "unit": "it/s",
+           "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_max / steps,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": dict(workload_config("D"), chains_per_gpu=nch, chains_total=world * nch),
+           "run": {"l2": "X[:, iup] of every chain is L2 / shared-memory resident (stated; latency-bound regime)",
+                   "parallelism": f"{nch} chains per GPU on separate streams, {world} GPU(s), no communication",
+                   "algorithm": "cluster-mode fused trajectory kernel (one 16-CTA cluster per chain)",
+                   "mean_nuvar": float(np.mean(uvar)), "hmc_reject": float(np.mean(rej)),
+                   "chain_warmup_iterations": warm_iters},
+           "one_after_the_other": {"value": world * nch * steps / (seq_max * 1e-3), "unit": "it/s",
+                                   "concurrency_gain": seq_max / ms_max},
+           "gpu_launches": launches, "clocks": clk,
+           "roofline": None, "roofline_note": "latency-bound regime (X[:, iup] of a chain is a few MB, L2 / shared-memory "
+                                              "resident); the HBM roofline is reported on the default workload"}
+    if cpu_baseline:
+        rate, kind, m = cpu_reference_rate("D", 40, budget_s=12.0, warm_iters=150)
+        out["cpu_baseline"] = {"value": rate, "unit": "it/s", "cores": 1, "kind": kind,
+                               "sample": f"one chain, {m} sampling iterations after 150 warm-up iterations, 1 of "
+                                         f"{os.cpu_count()} host cores"}
+    return out
 
 
 def make_tall_on_device(torch, n_total, p, C, rank, world, seed):
@@ -434,33 +457,37 @@ def make_tall_on_device(torch, n_total, p, C, rank, world, seed):
     return dict(Xt=Xt, ld=ld, ymat=ymat, ybase=ybase, n_local=nl, K=K)
 
 
-def measure_tall(torch, a, dist, rank, world, local):
-    """Config E: one chain, rows sharded over the ranks. Strong scaling: total work fixed as N grows."""
+def measure_tall(torch, steps, warmup, n_total, dist, rank, world, local, cpu_baseline=True):
+    """Config E: ONE chain, rows sharded over the ranks, NCCL all-reduce of the gradient partials in every leapfrog
+    step. Strong scaling: total work fixed as N grows. Returns the result dict on rank 0, None elsewhere."""
     import htlr_b200
     from htlr_b200 import shard, synth
     w = WORKLOADS["E"]
-    n_total = a.n_total or w["n"]
+    n_total = n_total or w["n"]
     p, C = w["p"], w["C"]
     d = make_tall_on_device(torch, n_total, p, C, rank, world, w["seed"])
     K, nl = d["K"], d["n_local"]
     deltas, sig = synth.init_state(p, K, init="zero", seed=w["seed"] + 17)
-    total = a.warmup + a.steps + min(a.steps, 5)
+    psteps = min(steps, 5)
+    total = warmup + steps + psteps
     comm = None
     if world > 1:
         uid = shard.exchange_unique_id(dist, shard.nccl_unique_id)
         comm = shard.nccl_init(uid, rank, world, local)
-    kw = dict(HTLR_DEFAULTS)
+    kw = dict(HTLR_DEFAULTS, leap_step=w.get("leap_step", HTLR_DEFAULTS["leap_step"]))
     smp = htlr_b200.Sampler(p, K, nl, None, None, None, hmc_sgmcut=w["cut"], deltas=deltas, sigmasbt=sig, iters_h=0,
                             iters_rmc=total, device=local, seed=1000, nccl_comm=comm,
                             device_ptrs=(d["Xt"].data_ptr(), d["ld"], d["ymat"].data_ptr(), d["ybase"].data_ptr()),
                             **kw)
-    smp.run(a.warmup)
+    smp.run(warmup)
+    clocks = ClockSampler(local)
+    clocks.start()
     l0 = smp.launch_count
-    ms = time_chain(torch, smp, a.steps, dist)
+    ms = time_chain(torch, smp, steps, dist)
     launches = smp.launch_count - l0
+    clk = clocks.stop()
     smp.profile_enable(True)
     smp.profile_get(reset=True)
-    psteps = min(a.steps, 5)
     smp.run(psteps)
     pr = smp.profile_get()
     smp.profile_enable(False)
@@ -468,41 +495,100 @@ def measure_tall(torch, a, dist, rank, world, local):
     smp.close()
     if comm is not None:
         shard.nccl_destroy(comm)
+    del d
+    torch.cuda.empty_cache()
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t[0])
     if rank != 0:
-        return
+        return None
     peak, peak_src = measured_peak()
     ach = (pr["sweep_bytes"] / 1e9) / (pr["sweep_ms"] * 1e-3)
-    u = float(np.mean(out["mcuvar"][a.warmup + 1:a.warmup + 1 + a.steps]))
-    line = {"metric": "mcmc_iterations_per_sec", "value": a.steps / (ms_max * 1e-3), "unit": "it/s", "n_gpus": world,
-            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_max / a.steps, "higher_is_better": True,
+    u = float(np.mean(out["mcuvar"][warmup + 1:warmup + 1 + steps]))
+    L = HTLR_DEFAULTS["leap_L"]
+    # two X sweeps per leapfrog step are inherent when rows are sharded (the gradient of a column needs every rank's
+    # rows before the column can move): 2 (L+1) sweeps of this rank's 8 n_local u bytes (+ the detach sweep)
+    bound_bytes = 2.0 * (L + 1) * 8.0 * nl * u
+    it_s = steps / (ms_max * 1e-3)
+    line = {"metric": "mcmc_iterations_per_sec", "value": it_s, "unit": "it/s", "n_gpus": world,
+            "steps": steps, "warmup": warmup, "ms_per_step": ms_max / steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": w["desc"] if n_total == w["n"] else w["desc"].replace("n=200000", f"n={n_total}"),
-                       "regime": "full", "rows_per_rank": nl,
-                       "l2": "X shard (%.1f GB) is larger than the 126 MB L2; no flush needed" % (8e-9 * nl * (p + 1)),
-                       "parallelism": f"rows sharded over {world} rank(s), NCCL all-reduce (sum, f64) of the "
-                                      f"{p + 1}x{K} gradient partials + log-likelihood per gradient evaluation"
-                       if world > 1 else "1 GPU holds all rows",
-                       "algorithm": "two-sweep (lv sweep + gradient sweep per leapfrog step)", "mean_nuvar": u,
-                       "hmc_reject": float(np.mean(out["mchmcrej"][a.warmup + 1:a.warmup + 1 + a.steps]))},
-            "e2e": None, "e2e_note": "X is generated on the device (16 GB at full size); the host-buffer end-to-end "
-                                     "number is measured on the default workload",
-            "gpu_launches": launches,
+            "config": dict(workload_config("E"), n_total=n_total),
+            "run": {"rows_per_rank": nl,
+                    "l2": "X shard (%.1f GB) is larger than the 126 MB L2; no flush needed" % (8e-9 * nl * (p + 1)),
+                    "parallelism": f"rows sharded over {world} rank(s), NCCL all-reduce (sum, f64) of the "
+                                   f"{p + 1}x{K} gradient partials + log-likelihood per gradient evaluation"
+                    if world > 1 else "1 GPU holds all rows",
+                    "algorithm": "two-sweep (lv sweep + gradient sweep per leapfrog step)", "mean_nuvar": u,
+                    "hmc_reject": float(np.mean(out["mchmcrej"][warmup + 1:warmup + 1 + steps]))},
+            "gpu_launches": launches, "clocks": clk,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": None, "kernel": "k_lv_sweep + k_grad_sweep over this rank's row block",
+                         "traffic": None, "traffic_source": "not captured for this workload",
+                         "kernel": "k_lv_sweep + k_grad_sweep over this rank's row block",
                          "peak_source": peak_src, "launches_timed": pr["sweep_launches"],
                          "algorithmic_bytes_per_launch": pr["sweep_bytes"] / max(pr["sweep_launches"], 1),
-                         "sweep_share_of_step": pr["sweep_ms"] / max(pr["total_ms"], 1e-9)}}
-    if not a.no_cpu_baseline:
-        rate, kind, m = cpu_reference_rate("E", 3, budget_s=25.0, warm_iters=0)
+                         "sweep_share_of_step": pr["sweep_ms"] / max(pr["total_ms"], 1e-9),
+                         "two_sweep_bound": {"bytes_per_iteration_per_rank": bound_bytes,
+                                             "it_s_at_measured_peak": peak * 1e9 / bound_bytes,
+                                             "frac_iteration": it_s * bound_bytes / 1e9 / peak}}}
+    if cpu_baseline:
+        rate, kind, m = cpu_reference_rate("E", 3, budget_s=15.0, warm_iters=0)
         line["cpu_baseline"] = {"value": rate * E_CPU_ROWS / n_total, "unit": "it/s", "cores": 1, "kind": kind,
                                 "sample": f"{m} sampling iterations on a {E_CPU_ROWS}-row sample of the same law, scaled "
                                           f"linearly to n={n_total} (the reference's cost is linear in n); 1 of "
                                           f"{os.cpu_count()} host cores"}
-    print(json.dumps(line))
+    return line
+
+
+def sharded_parity(torch, dist, rank, world, local):
+    """A small chain row-sharded over all ranks (device Philox, identical keys on every rank) against the same chain
+    on rank 0 alone with the two-sweep algorithm: the accept history and the restricted-set sizes must be identical
+    and the coefficient trace equal to 1e-10 (norm-relative); every rank must hold the same trace bit for bit."""
+    import htlr_b200
+    from htlr_b200 import synth
+    n, p, C, iters_h, iters_rmc = 4000, 300, 3, 4, 8
+    d = synth.gendata_mlr(n, p, NC=C, seed=4242)
+    y = d["y"].copy()
+    y[:C] = np.arange(C)
+    X, ymat, ybase, K = synth.make_inputs(d["X"], y)
+    g = np.random.default_rng(4243)
+    deltas = np.asfortranarray(g.standard_normal((p + 1, K)) * 0.3)
+    v = synth.comp_vardeltas(deltas)[1:]
+    sig = np.r_[2000.0, (np.exp(-10.0) + v) / 2 / g.gamma((1 + K) / 2, size=p)]
+    args = dict(HTLR_DEFAULTS, p=p, K=K, n=n, X=X, ymat=ymat, ybase=ybase, deltas=deltas, sigmasbt=sig,
+                hmc_sgmcut=0.05, iters_h=iters_h, iters_rmc=iters_rmc, leap_L=12, leap_L_h=4, keep_warmup_hist=True)
+    T = iters_h + iters_rmc
+    s = htlr_b200.ShardedSampler(**args, dist=dist, device=local, seed=77)
+    s.run(T)
+    mine = s.fetch()
+    s.close()
+    # every rank's trace against rank 0's, bit for bit (replicated state evolves identically: no broadcast needed)
+    flat = np.concatenate([np.ravel(mine[k]) for k in ("mcdeltas", "mcsigmasbt", "mcloglike", "mcuvar", "mchmcrej")])
+    t0 = torch.from_numpy(flat.copy()).cuda()
+    dist.broadcast(t0, src=0)
+    same = torch.tensor([1.0 if np.array_equal(t0.cpu().numpy(), flat) else 0.0], device="cuda", dtype=torch.float64)
+    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    if rank != 0:
+        return None
+    one = htlr_b200.Sampler(**args, device=local, seed=77, algo=1)
+    one.run(T)
+    ref = one.fetch()
+    one.close()
+    den = float(np.max(np.abs(ref["mcdeltas"])))
+    rel = float(np.max(np.abs(mine["mcdeltas"] - ref["mcdeltas"])) / den)
+    rel_ll = float(np.max(np.abs(mine["mcloglike"] - ref["mcloglike"])) / np.max(np.abs(ref["mcloglike"])))
+    out = {"what": f"n={n} p={p} C={C}, {T} iterations (L=12), device Philox, rows sharded over {world} ranks with an NCCL "
+                   f"all-reduce of the gradient partials per leapfrog step vs the same chain on rank 0 alone (two-sweep)",
+           "mcuvar_identical": bool(np.array_equal(mine["mcuvar"], ref["mcuvar"])),
+           "mchmcrej_identical": bool(np.array_equal(mine["mchmcrej"], ref["mchmcrej"])),
+           "relerr_mcdeltas": rel, "relerr_mcloglike": rel_ll, "tolerance": 1e-10,
+           "all_ranks_bit_identical": bool(float(same[0]) == 1.0),
+           "accepted_proposals": int(T - float(np.sum(ref["mchmcrej"][1:]))),
+           "mean_nuvar": float(np.mean(ref["mcuvar"][1:]))}
+    out["ok"] = bool(out["mcuvar_identical"] and out["mchmcrej_identical"] and rel < 1e-10 and rel_ll < 1e-10
+                     and out["all_ranks_bit_identical"])
+    return out
 
 
 def main():
@@ -514,6 +600,8 @@ def main():
     ap.add_argument("--workload", default="C_full", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the default-cut (restricted) block")
+    ap.add_argument("--no-extra-blocks", action="store_true",
+                    help="skip the sharded_parity / E_row_sharded / D_chains blocks of the default workload's line")
     ap.add_argument("--algo", type=int, default=0, help="0 auto (fused when applicable), 1 two-sweep, 2 fused")
     ap.add_argument("--n-total", type=int, default=0, help="workload E only: total rows (default 200000)")
     ap.add_argument("--chains-per-gpu", type=int, default=4, help="workload D only")
@@ -545,14 +633,16 @@ def main():
         dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
         dist = dist_mod
 
-    if a.workload == "E":
-        measure_tall(torch, a, dist, rank, world, local)
-        if dist is not None:
-            dist.destroy_process_group()
-        return
-
-    if a.workload == "D":
-        measure_chains(torch, a, dist, rank, world, local)
+    if a.workload in ("E", "D"):
+        if a.workload == "E":
+            line = measure_tall(torch, a.steps, a.warmup, a.n_total, dist, rank, world, local, not a.no_cpu_baseline)
+        else:
+            line = measure_chains(torch, a.steps, a.warmup, a.chains_per_gpu, dist, rank, world, local,
+                                  not a.no_cpu_baseline)
+        if rank == 0:
+            line["e2e"] = None
+            line["e2e_note"] = "the host-buffer end-to-end number is measured on the default workload"
+            print(json.dumps(line))
         if dist is not None:
             dist.destroy_process_group()
         return
@@ -578,12 +668,11 @@ def main():
 
     secondary = None
     if not a.no_secondary and a.workload == "C_full" and rank == 0:
-        r2 = measure_workload(torch, "C_default", max(a.steps, 200), a.warmup, local, rank, None, want_profile=True)
-        secondary = {"workload": WORKLOADS["C_default"]["desc"], "value": max(a.steps, 200) / (r2["ms"] * 1e-3),
-                     "unit": "it/s", "ms_per_step": r2["ms"] / max(a.steps, 200), "mean_nuvar": r2["uvar"],
+        n2 = max(a.steps, 200)
+        r2 = measure_workload(torch, "C_default", n2, a.warmup, local, rank, None, want_profile=True)
+        secondary = {"workload": WORKLOADS["C_default"]["desc"], "value": n2 / (r2["ms"] * 1e-3),
+                     "unit": "it/s", "ms_per_step": r2["ms"] / n2, "mean_nuvar": r2["uvar"],
                      "hmc_reject": r2["rej"], "gpu_launches": r2["launches"],
-                     "kernel_time_share": (r2["prof"]["total_ms"] / r2["prof_steps"]) / (r2["ms"] / max(a.steps, 200))
-                     if r2["prof_steps"] else None,
                      "fused_phase_ms_per_launch_block0": {k: r2["prof"][k] / max(r2["prof_steps"], 1) for k in
                                                           ("fused_sweep_ms", "fused_barrier_ms", "fused_rowphase_ms")},
                      "note": "restricted regime: X[:,iup] is L2-resident, bound by launch/sync latency not HBM"}
@@ -611,6 +700,19 @@ def main():
     if dist is not None:
         dist.barrier()
 
+    # ---- the blocks for the paths that the replica measurement does not touch (every rank takes part)
+    blocks = {}
+    if a.workload == "C_full" and not a.no_extra_blocks:
+        if world > 1:
+            blocks["sharded_parity"] = sharded_parity(torch, dist, rank, world, local)
+        e_steps = max(3, min(a.steps, 5))
+        blocks["E_row_sharded"] = measure_tall(torch, e_steps, 3, a.n_total, dist, rank, world, local,
+                                               cpu_baseline=(world == 1 and not a.no_cpu_baseline))
+        blocks["D_chains"] = measure_chains(torch, max(a.steps, 100), a.warmup, a.chains_per_gpu, dist, rank, world, local,
+                                            cpu_baseline=(world == 1 and not a.no_cpu_baseline))
+        if dist is not None:
+            dist.barrier()
+
     if rank == 0:
         peak, peak_src = measured_peak()
         pr = res["prof"]
@@ -625,15 +727,17 @@ def main():
         # step); SURVEY 8d's B_iter,min = 8 n [m + (L+1) u] still counts the detach sweep
         bytes_min = 8.0 * n * ((0 if a.algo != 1 else m_detach) + (L + 1) * u)
         it_s_1gpu = a.steps / (res["ms"] * 1e-3)
+        tr = ncu_traffic("sweep")
         line = {
             "metric": "mcmc_iterations_per_sec", "value": value, "unit": "it/s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": w["desc"], "regime": "full" if w["cut"] <= 0 else "restricted",
-                       "l2": "X (%.0f MB) is larger than the 126 MB L2; no flush needed" % (8e-6 * n * nvar)
-                       if 8 * n * nvar > 126e6 else "X fits in L2 (stated; no flush: the sampler re-reads X by design)",
-                       "parallelism": "1 chain per GPU, no communication" if world > 1 else "1 chain, 1 GPU",
-                       "algorithm": "two-sweep (reference structure)" if a.algo == 1 else "fused one-sweep persistent trajectory kernel", "mean_nuvar": u, "hmc_reject": res["rej"]},
+            "config": workload_config(a.workload),
+            "run": {"l2": "X (%.0f MB) is larger than the 126 MB L2; no flush needed" % (8e-6 * n * nvar)
+                    if 8 * n * nvar > 126e6 else "X fits in L2 (stated; no flush: the sampler re-reads X by design)",
+                    "parallelism": "1 chain per GPU, no communication" if world > 1 else "1 chain, 1 GPU",
+                    "algorithm": "two-sweep (reference structure)" if a.algo == 1 else "fused one-sweep persistent trajectory kernel",
+                    "mean_nuvar": u, "hmc_reject": res["rej"], "chain_warmup_iterations": res["chain_warm"]},
             "e2e": {"value": e2e_value, "unit": "it/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "what": "htlr_fit_helper() with pinned host buffers: H2D of X/ymat/state, %d sampling iterations "
                             "(after %d warm-up), D2H of the full trace (pipelined behind the sampling, units of 8 "
@@ -642,13 +746,20 @@ def main():
             "gpu_launches": res["launches"],
             "clocks": clk,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": (ach / peak) if ach else None, "traffic": ncu_traffic("sweep"),
+                         "frac": (ach / peak) if ach else None,
+                         # the same algorithmic bytes over the driver-visible time of a whole iteration (every kernel of
+                         # it, graph replay): the kernel-level `frac` comes from a separate eager pass with events
+                         # around the sweep launches
+                         "frac_iteration": bytes_min * it_s_1gpu / 1e9 / peak,
+                         "traffic": tr, "traffic_source": "profiles/traffic.json (ncu --set full capture of the same "
+                                                          "kernel, committed; not re-measured in this run)" if tr else None,
                          "kernel": "k_lv_sweep + k_grad_sweep (X sweeps)" if a.algo == 1 else "k_traj (L+1 X sweeps per launch; no detach sweep: lv is carried across steps)", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": pr["sweep_bytes"] / max(pr["sweep_launches"], 1),
                          "launches_timed": pr["sweep_launches"], "frac_of_nominal_8TBs": (ach / 8000.0) if ach else None,
                          "fused_phase_ms_per_launch_block0": {k: pr[k] / max(res["prof_steps"], 1) for k in
                                                               ("fused_sweep_ms", "fused_barrier_ms", "fused_rowphase_ms")},
                          "iteration_level": {"bytes_two_sweep": bytes_two, "bytes_min_one_sweep": bytes_min,
+                                             "achieved_one_sweep_GBs": bytes_min * it_s_1gpu / 1e9,
                                              "achieved_two_sweep_GBs": bytes_two * it_s_1gpu / 1e9,
                                              "frac_two_sweep": bytes_two * it_s_1gpu / 1e9 / peak}},
         }
@@ -656,8 +767,10 @@ def main():
             line["default_cut"] = secondary
         if others:
             line["other_configs"] = others
+        for k, v in blocks.items():
+            line[k] = v
         if not a.no_cpu_baseline:
-            rate, kind, m = cpu_reference_rate(a.workload, 4, budget_s=25.0, warm_iters=0 if w["cut"] <= 0 else 150)
+            rate, kind, m = cpu_reference_rate(a.workload, 4, budget_s=25.0, warm_iters=0)
             line["cpu_baseline"] = {"value": rate, "unit": "it/s", "cores": 1, "kind": kind,
                                     "sample": f"{m} sampling iterations (L=50) of the same workload on 1 of "
                                               f"{os.cpu_count()} host cores (reference hot loops are single-threaded)"}
@@ -665,12 +778,14 @@ def main():
                 r2c, kind2, m2 = cpu_reference_rate("C_default", 400, budget_s=15.0, warm_iters=150)
                 secondary["cpu_baseline"] = {"value": r2c, "unit": "it/s", "cores": 1, "kind": kind2,
                                              "sample": f"{m2} sampling iterations after 150 warm-up iterations"}
+                secondary["ratio_to_cpu"] = secondary["value"] / r2c
             if others:
                 for name, wl_name, warm in (("A_colon_default_cut", "A", 150), ("B_default_cut", "B_default", 150),
                                             ("B_full", "B", 0)):
                     rc_, kind_, m_ = cpu_reference_rate(wl_name, 200, budget_s=8.0, warm_iters=warm)
                     others[name]["cpu_baseline"] = {"value": rc_, "unit": "it/s", "cores": 1, "kind": kind_,
                                                     "sample": f"{m_} sampling iterations after {warm} warm-up iterations"}
+                    others[name]["ratio_to_cpu"] = others[name]["value"] / rc_
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
