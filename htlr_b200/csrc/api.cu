@@ -540,13 +540,29 @@ void do_create(const htlr_cfg* cfg, const double* X, int64_t ldx, const double* 
   g.n = n; g.nvar = nvar; g.K = K;
   g.n_s = (int)round_up(n, 16);
   g.sm_count = dev.sm_count;
+  // Sweep grids: ONE full wave of resident blocks; a block walks its kernel's (row tile, column split) items with the
+  // grid's stride, and the number of splits is chosen so that every block gets the same number of items. (Grids of
+  // 1.06 / 1.32 waves - a second wave of a few blocks that cannot keep HBM busy - cost 30 % at 200000 rows:
+  // profiles/r02_ncu_tall_sweeps.txt.)
+  auto pick_split = [](int tiles, int wave, int max_split) {
+    int best = 1;
+    double best_eff = 0;
+    for (int sp = 1; sp <= max_split; ++sp) {
+      const int64_t items = (int64_t)tiles * sp;
+      const double eff = (double)items / ((double)((items + wave - 1) / wave) * wave);
+      if (eff > best_eff + 0.02) { best_eff = eff; best = sp; }   // a larger split only for a real gain
+    }
+    return best;
+  };
   g.lv_rt = (n + 511) / 512;
-  g.lv_cs = (int)std::max<int64_t>(1, std::min<int64_t>((4 * g.sm_count + g.lv_rt - 1) / g.lv_rt, 1024));
-  // residual tile of the gradient sweep: K * g_tr doubles <= 32 KB, so 6 blocks (48 warps) fit on an SM and keep
-  // ~100 KB of column loads in flight
-  g.g_tr = (int)std::min<int64_t>(g.n_s, std::max(256, (4096 / K) / 64 * 64));
+  const int lv_wave = g.sm_count * lv_sweep_blocks_per_sm(K);
+  g.lv_cs = pick_split(g.lv_rt, lv_wave, 64);
+  g.lv_grid = (int)std::min<int64_t>((int64_t)g.lv_rt * g.lv_cs, lv_wave);
+  g.g_tr = grad_sweep_tile_rows(K);
   g.g_rt = (n + g.g_tr - 1) / g.g_tr;
-  g.g_gx = std::max(1, (4 * g.sm_count + g.g_rt - 1) / g.g_rt);
+  const int g_wave = g.sm_count * grad_sweep_blocks_per_sm(K);
+  g.g_gx = pick_split(g.g_rt, g_wave, 1024);
+  g.g_grid = (int)std::min<int64_t>((int64_t)g.g_rt * g.g_gx, g_wave);
   g.e_grid = std::max(1, std::min((nvar + 255) / 256, 2 * g.sm_count));
 
   Bufs& b = h->b;
@@ -564,9 +580,14 @@ void do_create(const htlr_cfg* cfg, const double* X, int64_t ldx, const double* 
   }
   tr.mark("stream+arena");
   // ---- data
+  if (c.x_on_device && (reinterpret_cast<uintptr_t>(X) & 15))
+    FAIL(HTLR_E_ARG, "device-resident X must be 16-byte aligned (whole columns are fetched with bulk copies)");
   if (c.x_on_device) {
     if (ldx % 2) FAIL(HTLR_E_ARG, "device-resident X needs an even leading dimension");
     g.ld = ldx;
+    // the fused kernels copy whole row pairs, so row n of an odd n must be finite - make it zero
+    if ((n & 1) && ldx > n)
+      CU(cudaMemset2DAsync(const_cast<double*>(X) + n, ldx * sizeof(double), 0, sizeof(double), nvar, h->st));
     b.X = X;
   } else {
     g.ld = round_up(n, 16);

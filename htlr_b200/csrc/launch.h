@@ -32,10 +32,12 @@ struct Geom {
   // lv sweep: 256 threads x 2 rows per block
   int lv_rt;        // row tiles
   int lv_cs;        // max column splits (partial-sum slots)
+  int lv_grid;      // blocks: one full wave (a block walks (row tile, split) items with the grid's stride)
   // gradient sweep: 8 warps per block, one column per warp at a time
-  int g_tr;         // rows per tile
+  int g_tr;         // rows per tile (a block: 8 warps x PP*64 rows)
   int g_rt;         // row tiles
-  int g_gx;         // blocks per row tile
+  int g_gx;         // column groups per row tile
+  int g_grid;       // blocks: one full wave (a block walks (row tile, column group) items with the grid's stride)
   // elementwise kernels over the restricted set
   int e_grid;
   int sm_count;
@@ -103,6 +105,9 @@ void launch_softmax(const Geom& g, const Bufs& b, int what, const int* cnt, doub
 void launch_grad_sweep(const Geom& g, const Bufs& b, const int* idx, const int* cnt, const double* R,
                        double* gout, cudaStream_t st);
 // sums row-tile partials into g (only needed before an all-reduce; k_post does it itself otherwise)
+int lv_sweep_blocks_per_sm(int K);     // resident blocks per SM (occupancy query; current device)
+int grad_sweep_blocks_per_sm(int K);
+int grad_sweep_tile_rows(int K);       // rows one block of the gradient sweep covers
 void launch_gsum(const Geom& g, const Bufs& b, const int* cnt, double* gout, cudaStream_t st);
 void launch_post(const Geom& g, const Bufs& b, int s, int L, int g_is_summed, cudaStream_t st);
 void launch_energy(const Geom& g, const Bufs& b, int g_has_loglike, cudaStream_t st);

@@ -35,6 +35,10 @@ namespace htlr {
     case 2: { constexpr int KT = 2; __VA_ARGS__; } break; \
     case 3: { constexpr int KT = 3; __VA_ARGS__; } break; \
     case 4: { constexpr int KT = 4; __VA_ARGS__; } break; \
+    case 5: { constexpr int KT = 5; __VA_ARGS__; } break; \
+    case 6: { constexpr int KT = 6; __VA_ARGS__; } break; \
+    case 7: { constexpr int KT = 7; __VA_ARGS__; } break; \
+    case 8: { constexpr int KT = 8; __VA_ARGS__; } break; \
     default: { constexpr int KT = 0; __VA_ARGS__; } break; \
   }
 
@@ -249,66 +253,71 @@ __global__ void __launch_bounds__(256) k_lv_sweep(Geom g, Bufs b, int mode, cons
   int64_t* s_off = reinterpret_cast<int64_t*>(s_coef + (size_t)kLvChunk * K);  // [kLvChunk] column offsets (doubles)
   const ColSet cs = resolve_cols(g, b, mode, idx_in, cnt_in, coef_global);
   if (mode == 0) timeline_mark(b.ctl, 2);
-  const int s = blockIdx.x;
-  if (s == 0 && blockIdx.y == 0 && threadIdx.x == 0) b.ctl->cols_swept += (unsigned long long)cs.cnt;
-  if (s >= cs.slots) return;
-  const int c0 = (int)((int64_t)s * cs.cnt / cs.slots), c1 = (int)((int64_t)(s + 1) * cs.cnt / cs.slots);
-  const int i = blockIdx.y * 512 + 2 * threadIdx.x;
-  const bool active = i < g.n;
-  const bool tail = (i + 1 >= g.n);
-  double a0[KM], a1[KM];
-#pragma unroll
-  for (int k = 0; k < KM; ++k) { a0[k] = 0; a1[k] = 0; }
-  const double* Xi = b.X + (active ? i : 0);
+  if (blockIdx.x == 0 && threadIdx.x == 0) b.ctl->cols_swept += (unsigned long long)cs.cnt;
   const int nvar = g.nvar;
   constexpr int kU = 8;
-  for (int ch0 = c0; ch0 < c1; ch0 += kLvChunk) {
-    const int cn = min(kLvChunk, c1 - ch0);
-    __syncthreads();   // the previous chunk is consumed
-    for (int e = threadIdx.x; e < cn; e += blockDim.x) {
-      const int j = __ldg(cs.idx + ch0 + e);
-      s_off[e] = (int64_t)j * g.ld;
-      for (int k = 0; k < K; ++k)
-        s_coef[e * K + k] = cs.cg ? __ldg(cs.cg + (int64_t)k * nvar + j) : __ldg(b.dc + (int64_t)(ch0 + e) * K + k);
-    }
-    __syncthreads();
-    if (!active) continue;
-    int r = 0;
-    for (; r + kU <= cn; r += kU) {
-      double2 x[kU];
+  // The grid is ONE full wave of resident blocks (launch_lv_sweep); a block walks the (row tile, column split) items
+  // with the grid's stride, so every block gets the same number of items (the number of splits is chosen for that):
+  // a second, nearly empty wave of a few blocks cannot keep HBM busy and cost 30 % at 200000 rows.
+  const int items = g.lv_rt * cs.slots;
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    const int rt = item / cs.slots, s = item - rt * cs.slots;
+    const int c0 = (int)((int64_t)s * cs.cnt / cs.slots), c1 = (int)((int64_t)(s + 1) * cs.cnt / cs.slots);
+    const int i = rt * 512 + 2 * threadIdx.x;
+    const bool active = i < g.n;
+    const bool tail = (i + 1 >= g.n);
+    double a0[KM], a1[KM];
 #pragma unroll
-      for (int q = 0; q < kU; ++q) x[q] = ld_stream2(Xi + s_off[r + q]);
+    for (int k = 0; k < KM; ++k) { a0[k] = 0; a1[k] = 0; }
+    const double* Xi = b.X + (active ? i : 0);
+    for (int ch0 = c0; ch0 < c1; ch0 += kLvChunk) {
+      const int cn = min(kLvChunk, c1 - ch0);
+      __syncthreads();   // the previous chunk is consumed
+      for (int e = threadIdx.x; e < cn; e += blockDim.x) {
+        const int j = __ldg(cs.idx + ch0 + e);
+        s_off[e] = (int64_t)j * g.ld;
+        for (int k = 0; k < K; ++k)
+          s_coef[e * K + k] = cs.cg ? __ldg(cs.cg + (int64_t)k * nvar + j) : __ldg(b.dc + (int64_t)(ch0 + e) * K + k);
+      }
+      __syncthreads();
+      if (!active) continue;
+      int r = 0;
+      for (; r + kU <= cn; r += kU) {
+        double2 x[kU];
 #pragma unroll
-      for (int q = 0; q < kU; ++q) {
+        for (int q = 0; q < kU; ++q) x[q] = ld_stream2(Xi + s_off[r + q]);
+#pragma unroll
+        for (int q = 0; q < kU; ++q) {
+#pragma unroll
+          for (int k = 0; k < KM; ++k) {
+            if (k < K) {
+              const double c = s_coef[(r + q) * K + k];
+              a0[k] = fma(x[q].x, c, a0[k]);
+              a1[k] = fma(x[q].y, c, a1[k]);
+            }
+          }
+        }
+      }
+      for (; r < cn; ++r) {
+        const double2 x = ld_stream2(Xi + s_off[r]);
 #pragma unroll
         for (int k = 0; k < KM; ++k) {
           if (k < K) {
-            const double c = s_coef[(r + q) * K + k];
-            a0[k] = fma(x[q].x, c, a0[k]);
-            a1[k] = fma(x[q].y, c, a1[k]);
+            const double c = s_coef[r * K + k];
+            a0[k] = fma(x.x, c, a0[k]);
+            a1[k] = fma(x.y, c, a1[k]);
           }
         }
       }
     }
-    for (; r < cn; ++r) {
-      const double2 x = ld_stream2(Xi + s_off[r]);
+    if (!active) continue;
 #pragma unroll
-      for (int k = 0; k < KM; ++k) {
-        if (k < K) {
-          const double c = s_coef[r * K + k];
-          a0[k] = fma(x.x, c, a0[k]);
-          a1[k] = fma(x.y, c, a1[k]);
-        }
+    for (int k = 0; k < KM; ++k) {
+      if (k < K) {
+        double* o = b.lvpart + ((int64_t)s * K + k) * g.n_s + i;
+        if (tail) o[0] = a0[k];
+        else *reinterpret_cast<double2*>(o) = make_double2(a0[k], a1[k]);
       }
-    }
-  }
-  if (!active) return;
-#pragma unroll
-  for (int k = 0; k < KM; ++k) {
-    if (k < K) {
-      double* o = b.lvpart + ((int64_t)s * K + k) * g.n_s + i;
-      if (tail) o[0] = a0[k];
-      else *reinterpret_cast<double2*>(o) = make_double2(a0[k], a1[k]);
     }
   }
 }
@@ -392,71 +401,154 @@ __global__ void __launch_bounds__(256) k_softmax(Geom g, Bufs b, int what, const
 }
 
 // ------------------------------------------------------------------------------------------------
-// g[r, k] = sum_i X[i, idx[r]] * R[i, k]: one warp per column, residual tile staged in shared memory,
-// 128-bit column loads, lane-strided partial sums + xor-tree (deterministic).
+// g[r, k] = sum_i X[i, idx[r]] * R[i, k].
+// A block = 8 warps = 8 consecutive row sub-tiles of PP*64 rows; a lane keeps the residual of ITS rows (PP row pairs
+// x K classes) in registers for all the columns it sees - the first version staged the residual tile in shared
+// memory and read K * 16 bytes of it per 16 bytes of X, which at K = 4 is 70 % of an SM's shared-memory bandwidth at
+// HBM speed and held the sweep at 4.4 TB/s (ncu: profiles/r02_ncu_tall_sweeps.txt). All warps of the block take the
+// same CU columns at a time. The columns come through a THREAD-PRIVATE ring in shared memory filled with cp.async
+// (16 bytes per copy, kGradDepth passes of CU * PP copies per lane in flight: 192 KB per SM): with the loads held in
+// registers, two passes (128 KB per SM at 254 registers) were the most that fit and the sweep stayed at 4.9 TB/s,
+// 43 % of the stall samples waiting for the next pass's loads; a ring slot belongs to one thread, so the ring itself
+// needs no barrier. The warps reduce their CU*K dot products
+// over the lanes with a transposing butterfly (V-1 + 5-log2(V) shuffles instead of 5V), then over the 8 warps
+// through shared memory (double-buffered: one block barrier per CU columns). Fixed order everywhere: deterministic.
+// The grid is one full wave; a block walks (row tile, column group) items with the grid's stride (see k_lv_sweep).
+constexpr int kGradDepth = 3;   // passes in flight per thread
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+               : "memory");
+}
+template <int KT>
+struct GradShape {   // PP row pairs per lane, CU columns per pass: PP*KT <= 16 (residual: 64 registers), PP*CU <= 16
+  static constexpr int PP = KT == 0 ? 1 : (KT <= 2 ? 8 : (KT <= 4 ? 4 : 2));
+  static constexpr int CU = KT == 0 ? 2 : (KT > 4 ? 4 : 16 / PP);   // CU * K <= 32 dot products per pass
+};
+template <int KT>
+constexpr size_t grad_smem_bytes() {
+  return (size_t)kGradDepth * GradShape<KT>::CU * GradShape<KT>::PP * 256 * sizeof(double2);
+}
+constexpr int grad_rows_per_block(int K) { return 8 * 64 * (K > 8 ? 1 : (K <= 2 ? 8 : (K <= 4 ? 4 : 2))); }
+
 template <int KT>
 __global__ void __launch_bounds__(256) k_grad_sweep(Geom g, Bufs b, const int* idx, const int* cnt_in,
                                                      const double* __restrict__ R, double* __restrict__ gout) {
   constexpr int KM = KDim<KT>::kMax;
+  constexpr int PP = GradShape<KT>::PP, CU = GradShape<KT>::CU;
+  constexpr int V = CU * KM;                                         // dot products per pass
+  constexpr int VP = V <= 2 ? 2 : (V <= 4 ? 4 : (V <= 8 ? 8 : (V <= 16 ? 16 : 32)));
+  constexpr int LOG = VP == 2 ? 1 : (VP == 4 ? 2 : (VP == 8 ? 3 : (VP == 16 ? 4 : 5)));
+  static_assert(V <= 32, "at most 32 dot products per pass");
   const int K = KT > 0 ? KT : g.K;
-  extern __shared__ double sR[];  // [K][g_tr]
+  __shared__ double s_part[2][8][VP];
+  extern __shared__ __align__(16) double2 ring[];   // [kGradDepth][CU][PP][256 threads]
   const int cnt = *cnt_in;
-  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) b.ctl->cols_swept += (unsigned long long)cnt;
-  const int rt = blockIdx.y, i0 = rt * g.g_tr;
-  const int rows = min(g.g_tr, g.n - i0);
-  for (int e = threadIdx.x; e < K * g.g_tr; e += blockDim.x) {
-    const int k = e / g.g_tr, ii = e - k * g.g_tr;
-    sR[e] = ii < rows ? R[(int64_t)k * g.n_s + i0 + ii] : 0.0;
-  }
-  __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x == 0) b.ctl->cols_swept += (unsigned long long)cnt;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int pairs = (rows + 1) >> 1;
-  double* out = gout + (int64_t)rt * g.nvar * K;
-  for (int r = blockIdx.x * 8 + warp; r < cnt; r += gridDim.x * 8) {
-    const int j = __ldg(idx + r);
-    const double* xc = b.X + (int64_t)j * g.ld + i0;
-    double acc[KM];
+  const int vmine = lane >> (5 - LOG);                     // the value this lane holds after the transposing reduction
+  const bool vwriter = (lane & ((32 >> LOG) - 1)) == 0;
+  const int items = g.g_rt * g.g_gx;
+  int buf = 0;
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    const int rt = item / g.g_gx, cg = item - rt * g.g_gx;          // row tile (g_tr rows), column group
+    const int i0 = rt * g.g_tr + warp * (PP * 64);                   // this warp's sub-tile
+    // residual of this lane's rows (rows >= n hold 0 in R up to the stride n_s; beyond it: nothing to load)
+    double rr[PP][2][KM];
+    bool have[PP], odd_last[PP];
 #pragma unroll
-    for (int k = 0; k < KM; ++k) acc[k] = 0;
-    int m = lane;
-    // 8 x 512 B per warp in flight per pass (HBM latency under load is ~2.5 us)
-    for (; m + 224 < pairs; m += 256) {
-      double2 x[8];
+    for (int pp = 0; pp < PP; ++pp) {
+      const int row = i0 + 2 * (lane + 32 * pp);
+      have[pp] = row < g.n;
+      odd_last[pp] = row + 1 >= g.n;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) x[q] = ld_stream2(xc + 2 * (m + 32 * q));
+      for (int k = 0; k < KM; ++k) {
+        double2 t = make_double2(0.0, 0.0);
+        if (k < K && have[pp]) t = *reinterpret_cast<const double2*>(R + (int64_t)k * g.n_s + row);
+        rr[pp][0][k] = t.x;
+        rr[pp][1][k] = odd_last[pp] ? 0.0 : t.y;
+      }
+    }
+    const double* xt = b.X + i0 + 2 * lane;
+    double* out = gout + (int64_t)rt * g.nvar * K;
+    // pass i+D is requested as soon as pass i has been consumed; one commit group per pass, empty ones included, so
+    // that "all but the newest D-1 groups are complete" always means "the pass to consume has landed"
+    auto fetch = [&](int slot, int r0) {
+      if (r0 < cnt) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int mm = m + 32 * q;
-        if (2 * mm + 1 >= rows) x[q].y = 0;
+        for (int c = 0; c < CU; ++c) {
+          const int64_t off = (int64_t)__ldg(idx + min(r0 + c, cnt - 1)) * g.ld;
+#pragma unroll
+          for (int pp = 0; pp < PP; ++pp)
+            if (have[pp]) cp_async16(&ring[((slot * CU + c) * PP + pp) * 256 + threadIdx.x], xt + off + 64 * pp);
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    const int rstep = g.g_gx * CU;
+#pragma unroll
+    for (int d = 0; d < kGradDepth; ++d) fetch(d, cg * CU + d * rstep);
+    int slot = 0;
+    for (int r0 = cg * CU; r0 < cnt; r0 += rstep) {
+      asm volatile("cp.async.wait_group %0;" ::"n"(kGradDepth - 1) : "memory");
+      double2 x[CU][PP];
+#pragma unroll
+      for (int c = 0; c < CU; ++c)
+#pragma unroll
+        for (int pp = 0; pp < PP; ++pp)
+          x[c][pp] = have[pp] ? ring[((slot * CU + c) * PP + pp) * 256 + threadIdx.x] : make_double2(0.0, 0.0);
+      fetch(slot, r0 + kGradDepth * rstep);   // the slot is free again (its values sit in registers)
+      if (++slot == kGradDepth) slot = 0;
+      double v[VP];
+#pragma unroll
+      for (int c = 0; c < CU; ++c) {
 #pragma unroll
         for (int k = 0; k < KM; ++k) {
+          double a0 = 0, a1 = 0;
           if (k < K) {
-            const double2 rr = *reinterpret_cast<const double2*>(sR + k * g.g_tr + 2 * mm);
-            acc[k] = fma(x[q].x, rr.x, acc[k]);
-            acc[k] = fma(x[q].y, rr.y, acc[k]);
+#pragma unroll
+            for (int pp = 0; pp < PP; ++pp) {
+              a0 = fma(x[c][pp].x, rr[pp][0][k], a0);
+              a1 = fma(odd_last[pp] ? 0.0 : x[c][pp].y, rr[pp][1][k], a1);   // a pad row may hold anything
+            }
+          }
+          v[c * KM + k] = a0 + a1;
+        }
+      }
+#pragma unroll
+      for (int q = V; q < VP; ++q) v[q] = 0;
+      // transposing butterfly: the value set is halved at each of the first LOG levels, plain xor levels after
+      {
+        int half = VP / 2;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+          if (half >= 1) {
+            const bool upper = (lane & off) != 0;
+#pragma unroll
+            for (int q = 0; q < VP / 2; ++q) {
+              if (q < half) {
+                const double send = upper ? v[q] : v[q + half];
+                const double keep = upper ? v[q + half] : v[q];
+                v[q] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+              }
+            }
+            half >>= 1;
+          } else {
+            v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
           }
         }
       }
-    }
-    for (; m < pairs; m += 32) {
-      double2 x = ld_stream2(xc + 2 * m);
-      if (2 * m + 1 >= rows) x.y = 0;
+      if (vwriter) s_part[buf][warp][vmine] = v[0];
+      __syncthreads();
+      if (warp == 0 && lane < V) {
+        double a = s_part[buf][0][lane];
 #pragma unroll
-      for (int k = 0; k < KM; ++k) {
-        if (k < K) {
-          const double2 rr = *reinterpret_cast<const double2*>(sR + k * g.g_tr + 2 * m);
-          acc[k] = fma(x.x, rr.x, acc[k]);
-          acc[k] = fma(x.y, rr.y, acc[k]);
-        }
+        for (int ww = 1; ww < 8; ++ww) a += s_part[buf][ww][lane];
+        const int c = lane / KM, k = lane - c * KM;
+        if (k < K && r0 + c < cnt) out[(int64_t)(r0 + c) * K + k] = a;
       }
+      buf ^= 1;   // the next pass writes the other buffer: one barrier per pass is enough
     }
-#pragma unroll
-    for (int k = 0; k < KM; ++k) {
-      if (k < K) {
-        const double v = warp_sum(acc[k]);
-        if (lane == 0) out[(int64_t)r * K + k] = v;
-      }
-    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");   // (only empty groups are left)
   }
 }
 
@@ -733,19 +825,39 @@ void launch_select(const Geom& g, const Bufs& b, cudaStream_t st) {
 }
 void launch_begin(const Geom& g, const Bufs& b, cudaStream_t st) { k_begin<<<g.e_grid, 256, 0, st>>>(g, b); }
 
+static size_t lv_smem_bytes(int K) { return (size_t)kLvChunk * (K * sizeof(double) + sizeof(int64_t)); }   // <= 72 KB at K = 16
+
 void launch_lv_sweep(const Geom& g, const Bufs& b, int mode, const int* idx, const int* cnt,
                      const double* coef_global, cudaStream_t st) {
-  dim3 grid(g.lv_cs, g.lv_rt);
-  const size_t smem = (size_t)kLvChunk * (g.K * sizeof(double) + sizeof(int64_t));   // <= 36 KB at K = 16... see below
+  const size_t smem = lv_smem_bytes(g.K);
   DISPATCH_K(g.K, {
     static PerDeviceOnce configured;
     if (configured.needed()) {
       cudaFuncSetAttribute(k_lv_sweep<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
       configured.mark();
     }
-    k_lv_sweep<KT><<<grid, 256, smem, st>>>(g, b, mode, idx, cnt, coef_global);
+    k_lv_sweep<KT><<<g.lv_grid, 256, smem, st>>>(g, b, mode, idx, cnt, coef_global);
   });
 }
+
+// Resident blocks per SM of the two sweep kernels (the grids are sized to exactly one wave of them).
+int lv_sweep_blocks_per_sm(int K) {
+  int nb = 0;
+  DISPATCH_K(K, {
+    cudaFuncSetAttribute(k_lv_sweep<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_lv_sweep<KT>, 256, lv_smem_bytes(K));
+  });
+  return nb > 0 ? nb : 1;
+}
+int grad_sweep_blocks_per_sm(int K) {
+  int nb = 0;
+  DISPATCH_K(K, {
+    cudaFuncSetAttribute(k_grad_sweep<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grad_smem_bytes<KT>());
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_grad_sweep<KT>, 256, grad_smem_bytes<KT>());
+  });
+  return nb > 0 ? nb : 1;
+}
+int grad_sweep_tile_rows(int K) { return grad_rows_per_block(K); }
 void launch_softmax(const Geom& g, const Bufs& b, int what, const int* cnt, double* lv_out, double* R_out,
                     double* pred_out, double* loglike_out, cudaStream_t st) {
   const int grid = (g.n + 255) / 256;
@@ -753,15 +865,13 @@ void launch_softmax(const Geom& g, const Bufs& b, int what, const int* cnt, doub
 }
 void launch_grad_sweep(const Geom& g, const Bufs& b, const int* idx, const int* cnt, const double* R,
                        double* gout, cudaStream_t st) {
-  dim3 grid(g.g_gx, g.g_rt);
-  const size_t smem = (size_t)g.K * g.g_tr * sizeof(double);   // <= 64 KB by the choice of g_tr
   DISPATCH_K(g.K, {
-    static PerDeviceOnce configured;   // per instantiation: the residual tile can exceed the 48 KB default
+    static PerDeviceOnce configured;
     if (configured.needed()) {
-      cudaFuncSetAttribute(k_grad_sweep<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+      cudaFuncSetAttribute(k_grad_sweep<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grad_smem_bytes<KT>());
       configured.mark();
     }
-    k_grad_sweep<KT><<<grid, 256, smem, st>>>(g, b, idx, cnt, R, gout);
+    k_grad_sweep<KT><<<g.g_grid, 256, grad_smem_bytes<KT>(), st>>>(g, b, idx, cnt, R, gout);
   });
 }
 void launch_gsum(const Geom& g, const Bufs& b, const int* cnt, double* gout, cudaStream_t st) {

@@ -87,7 +87,11 @@ typedef struct htlr_cfg {
   int32_t algo;          /* HTLR_ALGO_* */
   uint64_t seed;         /* DEVICE rng: chain key */
   int32_t use_graph;     /* 1: replay one CUDA graph per thin-step (default), 0: eager launches */
-  int32_t x_on_device;   /* 1: X/ymat/ybase pointers passed to create are device pointers */
+  int32_t x_on_device;   /* 1: X/ymat/ybase pointers passed to create are device pointers. X is then BORROWED for
+                            the life of the handle (not copied);
+                            it must be 16-byte aligned with an even leading dimension, and for an odd n the
+                            pad row n of every column must hold a finite value (the fused kernels copy whole row
+                            pairs: create zeroes it when the leading dimension leaves room, i.e. ldx > n) */
   /* --- row sharding (tall X): all ranks pass the same p, K, seed; X/ymat/ybase hold local rows --- */
   void* nccl_comm;       /* ncclComm_t from htlr_cuda_nccl_init, or NULL for a single GPU */
   int32_t ars_inject_width; /* INJECT rng with ghs/neg: uniforms per (thin-step, feature) block */

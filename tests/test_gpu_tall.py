@@ -92,3 +92,52 @@ def test_device_resident_tall_inputs_give_the_same_chain():
     dev.close()
     for k in ("mcdeltas", "mcsigmasbt", "mcloglike", "mcuvar", "mchmcrej"):
         assert np.array_equal(a[k], b[k]), k
+
+
+
+@pytest.mark.parametrize("n,p,C", [(20500, 14, 2), (9100, 9, 9), (70001, 6, 5)], ids=["K1-five-tiles", "K8", "K4-35-tiles"])
+def test_gradient_sweep_shapes(n, p, C):
+    """Every register shape of the gradient sweep (rows per block 4096 / 2048 / 1024 / 512 for K <= 2 / 4 / 8 / 16) with
+    several row tiles, ragged last tile, odd n; restricted sets shorter than one pass of columns."""
+    args = problem(n, p, C, seed=n % 97)
+    gpu, ora = _pair(args)
+    g = np.random.default_rng(8)
+    for u in (1, 3, p + 1):
+        iup = np.sort(g.choice(p + 1, size=u, replace=False)).astype(np.int32)
+        deltas = np.asfortranarray(g.standard_normal((p + 1, C - 1)) * 0.2)
+        a, b = gpu.eval(iup, deltas), ora.eval(iup, deltas)
+        assert relerr(a["lv"], b["lv"]) < TOL
+        assert relerr(a["grad"], b["grad"]) < TOL
+        assert abs(a["loglike"] - b["loglike"]) < TOL * abs(b["loglike"])
+    gpu.close()
+
+
+def test_pad_row_of_device_resident_x_is_neutralised():
+    """with x_on_device and an odd n the kernels fetch whole row pairs; whatever sits in row n of the
+    caller's buffer (here NaN) must not reach the gradient. create zeroes the pad row when ldx leaves room for it."""
+    import torch
+    import htlr_b200
+    n, p, C = 301, 40, 3
+    args = problem(n, p, C, seed=5, iters_h=2, iters_rmc=6, leap_L=6, leap_L_h=2, hmc_sgmcut=0.0)
+    host = htlr_b200.Sampler(**args, seed=4)
+    host.run(8)
+    a = host.fetch()
+    host.close()
+    nvar, ld = p + 1, 304
+    Xt = torch.full((nvar, ld), float("nan"), dtype=torch.float64, device="cuda")
+    Xt[:, :n] = torch.from_numpy(np.ascontiguousarray(args["X"].T)).cuda()
+    ym = torch.from_numpy(np.ascontiguousarray(np.asarray(args["ymat"]).T)).cuda().contiguous()
+    yb = torch.from_numpy(np.ascontiguousarray(args["ybase"], dtype=np.int64)).cuda()
+    for algo in (0, 1):
+        dev = htlr_b200.Sampler(**dict(args, X=None, ymat=None, ybase=None), seed=4, algo=algo,
+                                device_ptrs=(Xt.data_ptr(), ld, ym.data_ptr(), yb.data_ptr()))
+        dev.run(8)
+        b = dev.fetch()
+        dev.close()
+        assert np.isfinite(b["mcdeltas"]).all()
+        if algo == 0:
+            for k in ("mcdeltas", "mcsigmasbt", "mcloglike", "mcuvar", "mchmcrej"):
+                assert np.array_equal(a[k], b[k]), k
+    with pytest.raises(htlr_b200.fit.HtlrCudaError):
+        htlr_b200.Sampler(**dict(args, X=None, ymat=None, ybase=None), seed=4,
+                          device_ptrs=(Xt.data_ptr() + 8, ld, ym.data_ptr(), yb.data_ptr()))   # misaligned X
