@@ -555,10 +555,14 @@ __global__ void __launch_bounds__(256) k_grad_sweep(Geom g, Bufs b, const int* i
 // Sum the row-tile partials (needed on its own only before an all-reduce).
 __global__ void k_gsum(Geom g, Bufs b, const int* cnt_in, double* gout) {
   const int cnt = *cnt_in, K = g.K;
-  const int64_t total = (int64_t)cnt * K;
-  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+  const int64_t total = (int64_t)cnt * K, all = (int64_t)g.nvar * K;
+  // the whole nvar*K buffer goes through the all-reduce (its length must be known when the graph is captured, the
+  // restricted-set size is not): entries past the restricted set are zeroed, so that nothing stale is ever re-summed
+  // in place (they used to grow by a factor of `world` per call)
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < all; e += (int64_t)gridDim.x * blockDim.x) {
     double a = 0;
-    for (int rt = 0; rt < g.g_rt; ++rt) a += b.gpart[(int64_t)rt * g.nvar * K + e];
+    if (e < total)
+      for (int rt = 0; rt < g.g_rt; ++rt) a += b.gpart[(int64_t)rt * g.nvar * K + e];
     gout[e] = a;
   }
   // the local log-likelihood rides along in the trailing slot (row-sharded all-reduce)
