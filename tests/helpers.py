@@ -7,11 +7,28 @@ DEFAULTS = dict(alpha=1.0, s=-10.0, eta=0.0, iters_rmc=6, iters_h=6, thin=1, lea
                 hmc_sgmcut=0.05, keep_warmup_hist=False, silence=1, legacy=False)
 
 
+# Gates (north_star: 1e-10 relative for the deterministic pieces and for a full trajectory with injected variates).
+# Whole chains with injected variates have identical accept histories on both sides, so they are held to the same
+# 1e-10; measured on the GPU: 1e-13..1e-11 (profiles/r02_parity_margins.json).
+TOL = 1e-10
+CHAIN_TOL = 1e-10
+
+
 def relerr(a, b):
     """Norm-wise relative error, the measure north_star's 1e-10 gate is stated in."""
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     den = np.max(np.abs(b))
     return float(np.max(np.abs(a - b)) / (den if den > 0 else 1.0))
+
+
+def record_margin(case, **values):
+    """HTLR_MARGINS_OUT=<file>: append the errors a test measured (how far inside its gate it is) as a JSON line."""
+    import json
+    import os
+    out = os.environ.get("HTLR_MARGINS_OUT")
+    if out:
+        with open(out, "a") as f:
+            f.write(json.dumps(dict(case=case, **{k: float(v) for k, v in values.items()})) + "\n")
 
 
 def problem(n, p, C, seed=0, init="random", ptype="t", scale=0.5, **over):

@@ -67,5 +67,5 @@ def test_cuda_reproduces_reference_chain_on_colon(algo):
     d, args, st = colon_case()
     s = htlr_b200.Sampler(**args, rng_mode=htlr_b200.fit.RNG_INJECT, algo=algo)
     s.run(24, **st)
-    check_against_golden(s.fetch(), d, 1e-8)
+    check_against_golden(s.fetch(), d, 1e-10)
     s.close()

@@ -73,7 +73,7 @@ def test_row_sharded_chain_matches_oracle(use_graph):
     for rank, out, uvar, n_rep in res:
         assert n_rep == 301
         for k in ("mcdeltas", "mcsigmasbt", "mcvardeltas", "mclogw", "mcloglike", "mcuvar", "mchmcrej"):
-            assert relerr(np.ravel(out[k]), np.ravel(b[k])) < 1e-8, (rank, k)
+            assert relerr(np.ravel(out[k]), np.ravel(b[k])) < 1e-10, (rank, k)
     # replicated state evolves bit-identically on both ranks (no broadcast needed)
     for k in res[0][1]:
         assert np.array_equal(res[0][1][k], res[1][1][k]), k
@@ -91,8 +91,8 @@ def test_row_sharded_device_rng_matches_single_gpu():
     for rank, out, uvar, n_rep in res:
         assert np.array_equal(out["mcuvar"], ref["mcuvar"])
         assert np.array_equal(out["mchmcrej"], ref["mchmcrej"])
-        assert relerr(out["mcdeltas"], ref["mcdeltas"]) < 1e-8
-        assert relerr(out["mcloglike"], ref["mcloglike"]) < 1e-8
+        assert relerr(out["mcdeltas"], ref["mcdeltas"]) < 1e-10
+        assert relerr(out["mcloglike"], ref["mcloglike"]) < 1e-10
 
 
 def test_one_process_drives_chains_on_two_devices():

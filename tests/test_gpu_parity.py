@@ -1,10 +1,10 @@
 """GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same seeded
 inputs. Tolerance: FP64, 1e-10 norm-wise relative for the deterministic pieces (north_star), a looser
-1e-8 for multi-iteration chains where leapfrog dynamics amplify rounding."""
+the same 1e-10 for multi-iteration chains with injected variates (identical accept histories)."""
 import numpy as np
 import pytest
 
-from tests.helpers import problem, relerr, streams
+from tests.helpers import CHAIN_TOL, problem, relerr, streams
 
 pytestmark = pytest.mark.gpu
 
@@ -73,7 +73,7 @@ def test_trajectory_matches_oracle(n, p, C, L, cut, algo):
     cut2 = cut * cut if cut > 0 else cut
     sel = np.nonzero(args["sigmasbt"] > cut2)[0]
     assert len(sel) == a["nuvar"]
-    tol = 1e-9 if L >= 30 else TOL  # 50 chained steps amplify the last-bit differences of the sums
+    tol = TOL   # north_star's gate, whatever the trajectory length
     assert relerr(a["deltas"], b["deltas"]) < tol
     assert relerr(a["momt"][sel], b["momt"][sel]) < tol
     assert relerr(a["lv"], b["lv"]) < tol
@@ -117,7 +117,7 @@ def test_chain_t_prior_injected(cfg, use_graph, algo):
     assert np.array_equal(sg["rej"], so["rej"])
     a, b = gpu.fetch(), ora.fetch()
     for k in ("mcdeltas", "mcsigmasbt", "mcvardeltas", "mclogw", "mcloglike", "mcuvar", "mchmcrej"):
-        assert relerr(np.ravel(a[k]), np.ravel(b[k])) < 1e-8, k
+        assert relerr(np.ravel(a[k]), np.ravel(b[k])) < CHAIN_TOL, k
     if cfg.get("leap_step", 0) > 0.5:
         assert b["mchmcrej"].sum() > 0  # the rejection / restore path was exercised
     gpu.close()
@@ -138,7 +138,7 @@ def test_chain_ars_priors_injected(ptype, C, algo):
     ora.run(T)
     a, b = gpu.fetch(), ora.fetch()
     for k in ("mcdeltas", "mcsigmasbt", "mcvardeltas", "mcloglike", "mcuvar", "mchmcrej"):
-        assert relerr(np.ravel(a[k]), np.ravel(b[k])) < 1e-8, k
+        assert relerr(np.ravel(a[k]), np.ravel(b[k])) < CHAIN_TOL, k
     gpu.close()
 
 
@@ -252,7 +252,7 @@ def test_fused_and_two_sweep_chains_agree():
     for o in outs[1:]:
         assert np.array_equal(outs[0]["mcuvar"], o["mcuvar"])
         assert np.array_equal(outs[0]["mchmcrej"], o["mchmcrej"])
-        assert relerr(outs[0]["mcdeltas"], o["mcdeltas"]) < 1e-8
+        assert relerr(outs[0]["mcdeltas"], o["mcdeltas"]) < CHAIN_TOL
 
 
 def test_fused_rejected_when_not_applicable():

@@ -96,7 +96,7 @@ def test_host_cpp_chain_matches_oracle_and_ctypes():
     ora.run(9)
     b = ora.fetch()
     for k in ("mcdeltas", "mcsigmasbt", "mcvardeltas", "mclogw", "mcloglike", "mcuvar", "mchmcrej"):
-        assert relerr(np.ravel(out[k]), np.ravel(b[k])) < 1e-8, k
+        assert relerr(np.ravel(out[k]), np.ravel(b[k])) < 1e-10, k
     assert relerr(out["DDNloglike"].ravel(), b["DDNloglike"]) < 1e-12
     # device RNG: the C++ host and the ctypes mirror give the very same chain for the same key
     r, out2 = run_host(a, seed=123)
