@@ -463,7 +463,8 @@ void check_device_error(htlr_handle* h) {
     case kErrArs:
       switch (c.err_detail) {
         case 1: FAIL(HTLR_E_SAMPLER, "Error in adaptive rejection sampling:\nthe first tangent point doesn't have positive probability.\n");
-        case 2: FAIL(HTLR_E_SAMPLER, "Error in Rejection Sampling:\n'max_nhull' is set too small, or your log-PDF is NOT concave.\n");
+        case 2: FAIL(HTLR_E_SAMPLER, "Error in Rejection Sampling:\n'max_nhull' is set too small, or your log-PDF is NOT concave.\n"
+                                     "(device engine: 16 hulls per feature, 32 for logw; the reference's default is 1000)\n");
         case 3: FAIL(HTLR_E_SAMPLER, "Error: in C function 'sample_elin':\nthe exp linear function integrates to NAN/INFINITY\n");
         default: FAIL(HTLR_E_SAMPLER, "adaptive rejection sampling did not terminate");
       }
@@ -1285,6 +1286,19 @@ int htlr_cuda_profile_get(htlr_handle* h, htlr_profile* out, int32_t reset) {
 }
 
 int64_t htlr_cuda_launch_count(const htlr_handle* h) { return h ? h->launches : 0; }
+
+int64_t htlr_cuda_ars_table_full(htlr_handle* h) {
+  if (!h) return -1;
+  int64_t out = -1;
+  guarded(h, [&] {
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaStreamSynchronize(h->st));
+    unsigned long long v = 0;
+    CU(cudaMemcpy(&v, reinterpret_cast<char*>(h->b.ctl) + offsetof(Ctl, ars_full), sizeof(v), cudaMemcpyDeviceToHost));
+    out = (int64_t)v;
+  });
+  return out;
+}
 
 int htlr_cuda_fit(const htlr_cfg* cfg, const double* X, int64_t ldx, const double* ymat, const int64_t* ybase,
                   const double* deltas0, const double* sigmasbt0, const htlr_inject* inject, htlr_tick_fn tick,

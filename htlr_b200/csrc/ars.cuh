@@ -33,6 +33,7 @@ enum ArsStatus : int {
   kArsBadPiece = 3,      // "the exp linear function integrates to NAN/INFINITY" (ars.cpp:391-398)
   kArsNoUniforms = 4,    // injected uniform block exhausted
   kArsStuck = 5,         // guard: more than kArsMaxTries proposals
+  kArsOkTableFull = 64,  // standalone hook only: a valid draw, but the hull table filled up on the way (see insert())
 };
 
 constexpr int kArsMaxTries = 4096;
@@ -113,8 +114,9 @@ struct ArsWarp {
   Eval& ev;
   Unif& un;
   int n_eval, n_unif;
+  bool full;       // the table filled up during this draw: later rejected points were not inserted
 
-  __device__ ArsWarp(Eval& e, Unif& u) : ev(e), un(u) {
+  __device__ ArsWarp(Eval& e, Unif& u) : ev(e), un(u), full(false) {
     lane = threadIdx.x & (W - 1);
     base = (threadIdx.x & 31) & ~(W - 1);
     mask = W == 32 ? 0xffffffffu : (0xffffu << base);
@@ -127,8 +129,12 @@ struct ArsWarp {
   __device__ __forceinline__ void relog() { H.lw = ars_logint(H.f, H.df, H.t, H.lo, H.hi); }
 
   // update_hulls(h, x, f, df), ars.cpp:22-119
+  // The reference's table holds max_nhull = 1000 hulls and update_hulls() returns silently once it is full
+  // (ars.cpp:26): the sampler stays exact, the envelope just stops tightening. Same semantics here with a table of
+  // W hulls (16 per feature, 32 for logw; the reference's targets need at most 13 - asserted in the tests); draws that
+  // got there are counted (Ctl::ars_full, htlr_cuda_ars_table_full) instead of passing unnoticed.
   __device__ void insert(int h, double x, double f, double df) {
-    if (nh == kArsCap) return;
+    if (nh == kArsCap) { full = true; return; }
     const double th = shfl_d(H.t, h);
     int lh, rh;
     if (x > th) {

@@ -45,6 +45,7 @@ struct Ctl {
   int ars_width;
   // errors
   int err, err_detail;
+  unsigned long long ars_full;   // ARS draws (ghs / neg variances, logw) whose hull table filled up (ars.cuh, insert())
   // X columns swept so far (lv + gradient sweeps), for the roofline arithmetic
   unsigned long long cols_swept;
   // fused trajectory kernel, block 0: SM cycles spent in the column sweep, the two grid barriers and the

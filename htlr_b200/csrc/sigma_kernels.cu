@@ -151,6 +151,7 @@ __global__ void __launch_bounds__(256, 3) k_sigma_ars(Geom g, Bufs b) {
       }
       ArsWarp<SgmTarget, ArsUniforms, kArsGroup> ars(tg, un);
       status = ars.sample(x0, x);
+      if (ars.full && lane == 0) atomicAdd(&ctl->ars_full, 1ull);
     }
     if (status != kArsOk) {
       if (lane == 0) set_err(ctl, status == kArsNoUniforms ? kErrInjectArs : kErrArs, status);
@@ -206,10 +207,12 @@ __global__ void __launch_bounds__(1024) k_logw(Geom g, Bufs b) {
     ArsArrayUniforms un{b.inj_ars + blk * ctl->ars_width, blk < ctl->n_ars_blocks ? ctl->ars_width : 0, 0};
     ArsWarp<LogwEval, ArsArrayUniforms> ars(ev, un);
     status = ars.sample(x0, x);
+    if (ars.full && threadIdx.x == 0) atomicAdd(&ctl->ars_full, 1ull);
   } else {
     ArsKeyedUniforms un{ctl->seed, ctl->step, kRngLogwArs, 0u, 0u};
     ArsWarp<LogwEval, ArsKeyedUniforms> ars(ev, un);
     status = ars.sample(x0, x);
+    if (ars.full && threadIdx.x == 0) atomicAdd(&ctl->ars_full, 1ull);
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -235,14 +238,16 @@ __global__ void __launch_bounds__(256) k_ars_batch(int kind, int m, const double
       ArsWarp<SgmTarget, ArsArrayUniforms, kArsGroup> ars(tg, un);
       status = ars.sample(x0, x);
       nu = ars.n_unif; ne = ars.n_eval;
+      if (status == kArsOk && ars.full) status = kArsOkTableFull;
     } else {
       ArsKeyedUniforms un{seed, step, kRngArs, (uint32_t)(q + 1), 0u};
       ArsWarp<SgmTarget, ArsKeyedUniforms, kArsGroup> ars(tg, un);
       status = ars.sample(x0, x);
       nu = ars.n_unif; ne = ars.n_eval;
+      if (status == kArsOk && ars.full) status = kArsOkTableFull;
     }
     if (lane == 0) {
-      x_out[q] = status == kArsOk ? x : NAN;
+      x_out[q] = (status == kArsOk || status == kArsOkTableFull) ? x : NAN;
       if (n_unif) n_unif[q] = nu;
       if (n_eval) n_eval[q] = ne;
       if (status_out) status_out[q] = status;

@@ -267,6 +267,11 @@ class Sampler:
     def launch_count(self):
         return _lib.lib().htlr_cuda_launch_count(self.h)
 
+    @property
+    def ars_table_full(self):
+        """ARS draws of this chain whose hull table (16 per feature, 32 for logw) filled up; see htlr_cuda.h."""
+        return _lib.lib().htlr_cuda_ars_table_full(self.h)
+
 
 def htlr_fit_helper(p, K, n, X, ymat, ybase, ptype, alpha, s, eta, iters_rmc, iters_h, thin, leap_L, leap_L_h,
                     leap_step, hmc_sgmcut, deltas, sigmasbt, keep_warmup_hist, silence, legacy, *, device=0,

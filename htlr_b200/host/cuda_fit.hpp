@@ -43,6 +43,18 @@ struct FitOutput {
   std::vector<double> mcloglike, mcuvar, mchmcrej;  // H x 1
 };
 
+// A host random-number stream in the REFERENCE's consumption order (the Rcpp glue points these at R's own
+// generator: R::rnorm, R::runif, R::rgamma): per thin-step u*K standard normals for the momenta, feature-major
+// (GenMomt, gibbs.cpp:441-460), one uniform for the Metropolis test (gibbs.cpp:90), then p gamma variates of shape
+// (alpha + K)/2 in feature order (spl_sgm_ig, utils.cpp:29-33). With it a fit consumes the host's stream exactly as the
+// reference's C++ sampler does, so set.seed() gives the reference's chain to rounding. u is only known once the
+// previous iteration's variances exist, so this mode runs one iteration per device call (slow; meant for checks). The
+// ARS priors and the logw update draw a data-dependent number of uniforms: t prior with eta = 0 and thin = 1 only.
+struct HostRng {
+  std::function<double()> norm, unif;
+  std::function<double(double)> gamma;   // shape -> Gamma(shape, 1)
+};
+
 // Extras the CUDA path needs beyond the 22 reference arguments.
 struct DeviceOptions {
   int device = 0;
@@ -51,6 +63,7 @@ struct DeviceOptions {
   bool use_graph = true;
   void* nccl_comm = nullptr;    // row-sharded X: communicator from htlr_cuda_nccl_init
   int ars_inject_width = 0;
+  const HostRng* host_rng = nullptr;   // draw every variate from the host's stream, in the reference's order
 };
 
 class CudaFit {
@@ -63,7 +76,7 @@ class CudaFit {
           double alpha, double s, double eta, int iters_rmc, int iters_h, int thin, int leap_L, int leap_L_h,
           double leap_step, double hmc_sgmcut, const double* deltas, const double* sigmasbt, bool keep_warmup_hist,
           int silence, bool legacy, const DeviceOptions& opt = DeviceOptions(), const htlr_inject* inject = nullptr)
-      : inject_(inject) {
+      : inject_(inject), host_rng_(opt.host_rng) {
     cfg_ = htlr_cfg{};
     cfg_.struct_size = sizeof(htlr_cfg);
     cfg_.abi_version = HTLR_CUDA_ABI_VERSION;
@@ -80,7 +93,10 @@ class CudaFit {
     cfg_.hmc_sgmcut = hmc_sgmcut;
     cfg_.keep_warmup_hist = keep_warmup_hist; cfg_.silence = silence; cfg_.legacy = legacy;
     cfg_.device = opt.device;
-    cfg_.rng_mode = inject ? HTLR_RNG_INJECT : HTLR_RNG_DEVICE;
+    cfg_.rng_mode = (inject || host_rng_) ? HTLR_RNG_INJECT : HTLR_RNG_DEVICE;
+    if (host_rng_ && (cfg_.ptype != HTLR_PRIOR_T || eta > 1e-10 || thin != 1))
+      throw CudaFitError(HTLR_E_ARG, "the host-order RNG mode supports the t prior with eta = 0 and thin = 1 only "
+                                     "(ARS and thinning consume a data-dependent number of variates)");
     cfg_.algo = opt.algo; cfg_.seed = opt.seed; cfg_.use_graph = opt.use_graph;
     cfg_.x_on_device = 0; cfg_.nccl_comm = opt.nccl_comm; cfg_.ars_inject_width = opt.ars_inject_width;
     const int rc = htlr_cuda_create(&cfg_, X, n, ymat, ybase, deltas, sigmasbt, &h_);
@@ -96,6 +112,33 @@ class CudaFit {
   // (gibbs.cpp:124). Injected variates are positional, so they run as one blocking call.
   void StartSampling(const Progress& progress = nullptr) {
     const int total = cfg_.iters_h + cfg_.iters_rmc;
+    if (host_rng_) {
+      // one iteration per call: the restricted set of iteration i is a function of the variances iteration i-1 left
+      const size_t nvar = (size_t)cfg_.p + 1, K = (size_t)cfg_.K;
+      const double cut = cfg_.hmc_sgmcut > 0 ? cfg_.hmc_sgmcut * cfg_.hmc_sgmcut : cfg_.hmc_sgmcut;   // gibbs.cpp:14
+      const double shape = (cfg_.alpha + cfg_.K) / 2;
+      std::vector<double> sig(nvar), normals, gammas((size_t)cfg_.p);
+      htlr_iter_stats st{};
+      for (int done = 0; done < total; ++done) {
+        check(htlr_cuda_get_state(h_, nullptr, nullptr, sig.data(), nullptr, nullptr, nullptr));
+        size_t u = 0;
+        for (size_t j = 0; j < nvar; ++j) u += sig[j] > cut;            // WhichUpdate, gibbs.cpp:156-170
+        normals.resize(u * K);
+        for (double& z : normals) z = host_rng_->norm();                  // GenMomt: j-major, k inner
+        double unif = host_rng_->unif();                                  // the accept test
+        for (double& gq : gammas) gq = host_rng_->gamma(shape);           // UpdateSigmasT, features 1..p
+        htlr_inject inj{};
+        inj.normals = normals.data(); inj.n_normals = (int64_t)normals.size();
+        inj.uniforms = &unif; inj.n_uniforms = 1;
+        inj.gammas = gammas.data(); inj.n_gammas = (int64_t)gammas.size();
+        check(htlr_cuda_run(h_, 1, &inj, &st));
+        if (cfg_.silence == 0)
+          std::printf("Iter%4d: deviance=%5.3f, logw=%6.2f, nuvar=%3.0f, hmcrej=%4.2f\n", done - cfg_.iters_h,
+                      -st.loglike / cfg_.n, st.logw, st.uvar, st.rej);
+        if (progress && progress(done + 1, &st, 1)) throw CudaFitError(HTLR_E_STATE, "interrupted");
+      }
+      return;
+    }
     const int unit = inject_ ? total : 8, depth = 64;
     std::vector<htlr_iter_stats> st(unit > 0 ? unit : 1);
     if (!inject_) { size_output(); collected_ = true; }
@@ -165,6 +208,7 @@ class CudaFit {
   htlr_cfg cfg_;
   htlr_handle* h_ = nullptr;
   const htlr_inject* inject_;
+  const HostRng* host_rng_ = nullptr;
   FitOutput out_;
   bool collected_ = false;
 };

@@ -7,10 +7,12 @@
 //
 // RNG: by default the chain uses the library's device Philox stream keyed from R's RNG (one unif_rand()
 // draw inside the RNGScope, so set.seed() still makes runs reproducible). With
-// options(HTLR.cuda.rng = "R") the glue draws the reference's own variates from R in the reference's
-// consumption order (gibbs.cpp:441-460 normals, :90 one uniform, utils.cpp:31 gammas) and injects them:
-// that needs the restricted-set size of every iteration in advance, which only the device knows, so it
-// runs one iteration per call with worst-case (p+1)*K normals — slow, meant for set.seed()-exact checks.
+// options(HTLR.cuda.rng = "R") the glue hands R's own generator to the host class (htlr::HostRng): every
+// variate is drawn from R in the reference's consumption order (gibbs.cpp:441-460 normals, :90 one uniform,
+// utils.cpp:31 gammas), one iteration per device call, so that set.seed() gives the reference's own chain to
+// rounding — slow, meant for checks; t prior with eta = 0 and thin = 1 only (cuda_fit.hpp explains why).
+// tests/test_rcpp_glue.py compiles this file against the repo's Rcpp/Armadillo stand-ins (test infrastructure) and
+// compares it, R-order mode included, with the reference's own htlr_fit_helper on the same streams.
 #include "RcppArmadillo.h"
 
 #include "cuda_fit.hpp"
@@ -25,7 +27,11 @@ Rcpp::List htlr_fit_helper(int p, int K, int n, arma::mat& X, arma::mat& ymat, a
   std::vector<int64_t> yb(ybase.begin(), ybase.end());  // arma::uword -> int64_t
   htlr::DeviceOptions opt;
   opt.device = Rcpp::as<int>(Rcpp::Function("getOption")("HTLR.cuda.device", 0));
-  opt.seed = (uint64_t)(unif_rand() * 9007199254740992.0);  // 53 bits from R's stream (RNGScope is open)
+  const bool r_order = Rcpp::as<std::string>(Rcpp::Function("getOption")("HTLR.cuda.rng", "device")) == "R";
+  htlr::HostRng from_r{[] { return R::rnorm(0.0, 1.0); }, [] { return R::runif(0.0, 1.0); },
+                       [](double shape) { return R::rgamma(shape, 1.0); }};
+  if (r_order) opt.host_rng = &from_r;
+  else opt.seed = (uint64_t)(unif_rand() * 9007199254740992.0);  // 53 bits from R's stream (RNGScope is open)
   htlr::FitOutput o;
   try {
     // silence = 1 below: progress is printed here with Rprintf, not by the host class with printf

@@ -241,6 +241,13 @@ void* htlr_cuda_stream(htlr_handle* h);                 /* cudaStream_t all work
 int htlr_cuda_profile_enable(htlr_handle* h, int32_t on); /* on: eager launches + per-kernel CUDA events */
 int htlr_cuda_profile_get(htlr_handle* h, htlr_profile* out, int32_t reset);
 int64_t htlr_cuda_launch_count(const htlr_handle* h);   /* kernels launched by this handle so far */
+/* Adaptive rejection sampling (ghs / neg variances, logw): the reference's hull table holds max_nhull = 1000 tangents
+ * and silently stops tightening the envelope once it is full (src/ars.cpp:26, src/ars.h:59-62); the device engine does
+ * the same with 16 tangents per feature (32 for logw). The draws stay exact either way. This returns how many draws of
+ * this handle filled their table (waits for the enqueued iterations; -1 on error): 0 on every workload seen so far -
+ * the reference's targets need at most 13. The step-out phase running out of tangents is an error, as in the
+ * reference (ars.cpp:155-160, 187-193). */
+int64_t htlr_cuda_ars_table_full(htlr_handle* h);
 int htlr_cuda_sync(htlr_handle* h);
 /* enqueue n_iters iterations without synchronising or copying stats (bench timed region) */
 int htlr_cuda_run_async(htlr_handle* h, int32_t n_iters);

@@ -259,9 +259,20 @@ def comp_lsl(A):
 
 def ref_fit(p, K, n, X, ymat, ybase, ptype, alpha, s, eta, iters_rmc, iters_h, thin, leap_L, leap_L_h,
             leap_step, hmc_sgmcut, deltas, sigmasbt, keep_warmup_hist=False, silence=1, legacy=False,
-            normals=None, uniforms=None, gammas=None):
-    """The reference's own htlr_fit_helper (main.cpp:7-25) compiled verbatim against the shims."""
-    r = _ref_lib("libhtlr_ref.so")
+            normals=None, uniforms=None, gammas=None, impl="reference", options=None):
+    """The reference's own htlr_fit_helper (main.cpp:7-25) compiled verbatim against the shims (impl="reference"),
+    or - same C entry point, same variate hooks - the repo's Rcpp glue above the CUDA library (impl="glue",
+    oracle/_glue/libhtlr_glue_test.so; `options` = R options for it, e.g. {"HTLR.cuda.rng": "R"})."""
+    if impl == "glue":
+        path = os.path.join(_HERE, "_glue", "libhtlr_glue_test.so")
+        if not os.path.exists(path):
+            raise RuntimeError("oracle/_glue/libhtlr_glue_test.so not built (make -C oracle glue)")
+        r = ctypes.CDLL(path)
+        r.htlr_ref_set_option.argtypes = [ctypes.c_char_p, ctypes.c_char_p]
+        for k in ("HTLR.cuda.rng", "HTLR.cuda.device"):
+            r.htlr_ref_set_option(k.encode(), str((options or {}).get(k, "")).encode())
+    else:
+        r = _ref_lib("libhtlr_ref.so")
     if r is None:
         raise RuntimeError("oracle/_ref/libhtlr_ref.so not built (needs /root/reference at build time)")
     r.htlr_ref_last_error.restype = ctypes.c_char_p

@@ -117,6 +117,39 @@ class NumericVector {
   std::vector<double> v_;
 };
 
+// getOption(), as<>, checkUserInterrupt: what the repo's own Rcpp glue (htlr_b200/host/rcpp_glue.cpp) uses beyond the
+// reference's sources. Options come from a map the test harness fills (htlr_ref_set_option).
+struct RObject {
+  std::string text;
+};
+}  // namespace Rcpp
+namespace rshim {
+std::map<std::string, std::string>& options();   // defined in the *_ref_api.cpp translation unit
+}
+namespace Rcpp {
+class Function {
+ public:
+  explicit Function(const char* name) : name_(name) {}
+  template <class T>
+  RObject operator()(const char* key, const T& fallback) const {
+    if (name_ != "getOption") throw Rcpp::exception(("shim: unsupported R function " + name_).c_str());
+    auto it = rshim::options().find(key);
+    if (it != rshim::options().end()) return RObject{it->second};
+    std::ostringstream os;
+    os << fallback;
+    return RObject{os.str()};
+  }
+ private:
+  std::string name_;
+};
+template <class T>
+T as(const RObject& o);
+template <>
+inline int as<int>(const RObject& o) { return std::stoi(o.text); }
+template <>
+inline std::string as<std::string>(const RObject& o) { return o.text; }
+inline void checkUserInterrupt() {}
+
 inline NumericVector runif(int n) {
   NumericVector o(n);
   for (int i = 0; i < n; ++i) o[i] = unif_rand();

@@ -148,6 +148,7 @@ class Col : public Mat {
   Col(const Mat& m) : Mat(m) { n_rows = n_elem; n_cols = 1; }
   Col(const Rcpp::NumericVector& v) : Mat(v.begin(), (uword)v.size(), 1) {}
   Col(const double* p, uword n) : Mat(p, n, 1) {}
+  Col(const std::vector<double>& v) : Mat(v.data(), v.size(), 1) {}
 };
 typedef Col vec;
 typedef Col colvec;
@@ -157,6 +158,7 @@ class Row : public Mat {
   Row() = default;
   explicit Row(uword n) : Mat(1, n) {}
   Row(const Mat& m) : Mat(m) { n_cols = n_elem; n_rows = 1; }
+  Row(const std::vector<double>& v) : Mat(v.data(), 1, v.size()) {}
 };
 typedef Row rowvec;
 
@@ -165,6 +167,7 @@ class Cube {
   uword n_rows = 0, n_cols = 0, n_slices = 0, n_elem = 0;
   Cube() = default;
   Cube(uword r, uword c, uword s, fill::fill_zeros) : n_rows(r), n_cols(c), n_slices(s), n_elem(r * c * s), mem_(r * c * s, 0.0) {}
+  Cube(const double* p, uword r, uword c, uword s) : n_rows(r), n_cols(c), n_slices(s), n_elem(r * c * s), mem_(p, p + r * c * s) {}
   struct Slice {
     Cube* q;
     uword s;

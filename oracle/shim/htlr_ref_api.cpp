@@ -15,12 +15,15 @@ Rcpp::List htlr_fit_helper(int p, int K, int n, arma::mat& X, arma::mat& ymat, a
                            int iters_h, int thin, int leap_L, int leap_L_h, double leap_step,
                            double hmc_sgmcut, arma::mat& deltas, arma::vec& sigmasbt,
                            bool keep_warmup_hist, int silence, bool legacy);
+#ifndef HTLR_GLUE_ONLY   // (-DHTLR_GLUE_ONLY: this file around the repo's own Rcpp glue instead of the reference's main.cpp:
+                         // only the htlr_fit_helper entry point exists then - tests/test_rcpp_glue.py)
 Rcpp::List std_helper(const arma::mat& A);
 arma::vec comp_vardeltas(const arma::mat& deltas);
 arma::vec comp_lsl(arma::mat& A);
 double log_normcons(arma::mat& A);
 Rcpp::List gendata_FAM_helper(int n, arma::mat& muj, const arma::mat& muj_rep, const arma::mat& A,
                               double sd_g, bool stdx);
+#endif
 
 namespace {
 struct Streams {
@@ -81,6 +84,10 @@ rshim::Hooks& rshim::hooks() {
   static Hooks h;
   return h;
 }
+std::map<std::string, std::string>& rshim::options() {
+  static std::map<std::string, std::string> o;
+  return o;
+}
 
 extern "C" {
 
@@ -93,6 +100,10 @@ struct ref_cfg {
 };
 
 const char* htlr_ref_last_error() { return g_err.c_str(); }
+// options(name = value) for the code under test; an empty value removes the option
+void htlr_ref_set_option(const char* name, const char* value) {
+  if (value && *value) rshim::options()[name] = value; else rshim::options().erase(name);
+}
 const char* htlr_ref_log() { return g_log.c_str(); }
 
 // Any of the three stream pointers may be null: that stream then comes from an internal generator
@@ -144,6 +155,7 @@ int htlr_ref_fit(const ref_cfg* c, const double* X, const double* ymat, const in
   return 0;
 }
 
+#ifndef HTLR_GLUE_ONLY
 // The reference's exported helpers with restatable known-answer tests (tests/testthat/test-util.r).
 void htlr_ref_comp_vardeltas(const double* d, int32_t rows, int32_t cols, double* out) {
   arma::mat m(d, rows, cols);
@@ -185,4 +197,5 @@ int htlr_ref_gendata_fam(int32_t n, int32_t p, int32_t nc, int32_t k, const doub
   }
   return 0;
 }
+#endif   // HTLR_GLUE_ONLY
 }

@@ -171,6 +171,45 @@ def test_ars_standalone_matches_cpu_engine():
             assert relerr(a["x"][same_path], b["x"][same_path]) < 1e-9
 
 
+def test_ars_hull_table_fills_like_the_reference_with_the_same_cap():
+    """SURVEY quirk / VERDICT r01 #8: the reference's update_hulls() silently stops inserting once max_nhull tangents
+    exist (ars.cpp:26); the device engine has the same semantics with a table of 16. Forced here with injected
+    uniforms whose accept variates are ~1 (every proposal rejected, so every try adds a tangent) for 20 tries: the
+    table fills, the draw is flagged (status 64 in the hook, htlr_cuda_ars_table_full in a chain) and still equals the
+    CPU engines' draw under the same cap."""
+    import htlr_b200
+    from oracle import oracle as O
+    g = np.random.default_rng(12)
+    m, tries = 4000, 40
+    u = g.random((m, 3 * tries))
+    u[:, 2:3 * 20:3] = 1.0 - 1e-13     # accept variate of the first 20 tries: log(ua) ~ -1e-13, rejected
+    u[:, 3 * 20 + 2::3] = 1e-9         # then accepted at once
+    for kind in ("ghs", "neg"):
+        vard = np.exp(g.uniform(np.log(1e-6), np.log(20), m))
+        a = htlr_b200.ars_sample(kind, vard, 2, 1.0, -10.0, uniforms=u)
+        assert np.isin(a["status"], (0, 64)).all()
+        assert (a["status"] == 64).mean() > 0.9 and a["n_eval"].max() >= 20   # the table did fill
+        assert np.isfinite(a["x"]).all()
+        for engine in ("port", "ref") if O.have_ref() else ("port",):
+            b = O.ars_batch(kind, vard, 2, 1.0, -10.0, u, max_nhull=16, engine=engine)
+            same_path = (a["n_unif"] == b["n_unif"]) & (a["n_eval"] == b["n_eval"])
+            assert same_path.mean() > 0.99, engine
+            assert relerr(a["x"][same_path], b["x"][same_path]) < 1e-9, engine
+        # with the reference's default cap the envelope keeps tightening: a different (equally exact) draw
+        c = O.ars_batch(kind, vard, 2, 1.0, -10.0, u, max_nhull=1000)
+        assert (np.abs(c["x"] - a["x"]) > 1e-9).mean() > 0.5
+
+
+def test_ars_table_never_fills_in_a_chain():
+    import htlr_b200
+    for ptype in ("ghs", "neg"):
+        args = problem(80, 400, 3, seed=3, ptype=ptype, iters_h=10, iters_rmc=30, leap_L=10, leap_L_h=3)
+        s = htlr_b200.Sampler(**args, seed=5)
+        s.run(40)
+        assert s.ars_table_full == 0
+        s.close()
+
+
 def test_device_rng_matches_host_twin():
     import htlr_b200
     from oracle import oracle as O
