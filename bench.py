@@ -361,6 +361,8 @@ def measure_chains(torch, steps, warmup, nch, dist, rank, world, local, cpu_base
         s.run(warm_iters + warmup)
     streams = [torch.cuda.ExternalStream(s.stream) for s in smps]
     ev = lambda: torch.cuda.Event(enable_timing=True)
+    clocks = ClockSampler(local)   # over both timed phases (the concurrent one alone can be shorter than a sample period)
+    clocks.start()
     # one after the other
     seq_ms = 0.0
     for s, st in zip(smps, streams):
@@ -370,8 +372,6 @@ def measure_chains(torch, steps, warmup, nch, dist, rank, world, local, cpu_base
     # together
     for s in smps:
         s.sync()
-    clocks = ClockSampler(local)
-    clocks.start()
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
@@ -697,6 +697,31 @@ def main():
                                          "seconds": dt, "value": 2000 / dt, "unit": "it/s",
                                          "mean_nuvar_sampling": float(np.mean(out["mcuvar"][1:])),
                                          "hmc_reject_sampling": float(np.mean(out["mchmcrej"][1:]))}
+        # N2: htlr_predict on the device from the resident trace of a whole default run - the one dense
+        # contraction of the path, n_ts x (p+1) x K*S in FP64 on the DMMA path - against the measured FP64 peaks
+        smp = htlr_b200.Sampler(**dict(args, iters_h=1000, iters_rmc=1000), device=local, seed=4243)
+        smp.run_async(2000)
+        smp.sync()
+        Xts = np.asfortranarray(args["X"])
+        t0 = time.perf_counter()
+        probs = smp.predict(Xts)
+        t_call = time.perf_counter() - t0
+        kms = []
+        for _ in range(3):
+            smp.predict(Xts)
+            kms.append(smp.predict_stats()[0])
+        flops = smp.predict_stats()[1]
+        smp.close()
+        pk = htlr_b200.fp64_peak(local)
+        km = sorted(kms)[1]
+        others["predict_on_device"] = {
+            "what": "htlr_predict (R/predict.R:28-92) of the %d training cases from the %d used samples of that run's "
+                    "resident trace: cbind(1, X_ts) %%*%% mcdeltas[, , used] on the FP64 tensor-core path (DMMA m8n8k4), "
+                    "log-sum-exp, mean over samples" % (Xts.shape[0], int(round(flops / (2.0 * Xts.shape[0] * Xts.shape[1] * args["K"])))),
+            "kernel_ms": km, "fp64_tflops": flops / (km * 1e-3) / 1e12, "flops": flops,
+            "fp64_peak_measured_tflops": pk, "frac_of_dmma_peak": flops / (km * 1e-3) / 1e12 / pk["dmma"],
+            "call_seconds_with_host_X_ts": t_call, "h2d_bytes": 8 * Xts.size,
+            "probs_row_sums_ok": bool(np.allclose(probs.sum(axis=1), 1.0, atol=1e-12))}
     if dist is not None:
         dist.barrier()
 
@@ -708,7 +733,7 @@ def main():
         e_steps = max(3, min(a.steps, 5))
         blocks["E_row_sharded"] = measure_tall(torch, e_steps, 3, a.n_total, dist, rank, world, local,
                                                cpu_baseline=(world == 1 and not a.no_cpu_baseline))
-        blocks["D_chains"] = measure_chains(torch, max(a.steps, 100), a.warmup, a.chains_per_gpu, dist, rank, world, local,
+        blocks["D_chains"] = measure_chains(torch, max(a.steps, 300), a.warmup, a.chains_per_gpu, dist, rank, world, local,
                                             cpu_baseline=(world == 1 and not a.no_cpu_baseline))
         if dist is not None:
             dist.barrier()

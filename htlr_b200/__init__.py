@@ -5,6 +5,6 @@ Public surface: `htlr_fit_helper` (the reference's entry point, same 22 argument
 the in-tree C-ABI library `libhtlr_cuda.so` (include/htlr_cuda.h); importing this package without it,
 or calling it without a B200, fails loudly — there is no CPU path.
 """
-from .fit import HtlrCudaError, Sampler, ars_sample, htlr_fit_helper, rng_dump, std  # noqa: F401
+from .fit import HtlrCudaError, Sampler, ars_sample, fp64_peak, htlr_fit_helper, rng_dump, std  # noqa: F401
 from . import _lib, shard  # noqa: F401
 from .shard import ShardedSampler  # noqa: F401

@@ -241,6 +241,7 @@ struct htlr_handle {
   cudaStream_t st_copy = nullptr;
   int slices_collected = 0;
   unsigned long long ph_base[4] = {0, 0, 0, 0};
+  double last_predict_ms = 0, last_predict_flops = 0;   // kernels of the last htlr_cuda_predict call (device time)
 
   // Device memory comes from a few large chunks (one cudaMalloc / cudaFree each): creating and destroying a
   // handle then costs a handful of driver calls instead of ~50, which is what the end-to-end time of a short
@@ -1185,16 +1186,31 @@ int htlr_cuda_predict(htlr_handle* h, const double* X_ts, int64_t ldx, int32_t n
     // scratch lives outside the handle's arena: test sets come and go
     const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)S, ((size_t)256 << 20) / (sizeof(double) * n_ts * K)));
     double *dA = nullptr, *dLV = nullptr, *dAcc = nullptr, *dP = nullptr;
-    auto cleanup = [&] { cudaFree(dA); cudaFree(dLV); cudaFree(dAcc); cudaFree(dP); };
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    auto cleanup = [&] {
+      cudaFree(dA); cudaFree(dLV); cudaFree(dAcc); cudaFree(dP);
+      if (e0) cudaEventDestroy(e0);
+      if (e1) cudaEventDestroy(e1);
+    };
+    const int64_t lda = round_up(n_ts, 16);   // columns 128-byte aligned, pad rows zero (16-byte async copies)
     try {
-      CU(cudaMalloc((void**)&dA, sizeof(double) * (size_t)n_ts * nvar));
+      CU(cudaMalloc((void**)&dA, sizeof(double) * (size_t)lda * nvar));
+      if (lda != n_ts) CU(cudaMemsetAsync(dA, 0, sizeof(double) * (size_t)lda * nvar, h->st));
       CU(cudaMalloc((void**)&dLV, sizeof(double) * (size_t)n_ts * K * chunk));
       CU(cudaMalloc((void**)&dAcc, sizeof(double) * (size_t)n_ts * K));
       CU(cudaMalloc((void**)&dP, sizeof(double) * (size_t)n_ts * (K + 1)));
-      CU(cudaMemcpy2DAsync(dA, (size_t)n_ts * sizeof(double), X_ts, (size_t)ldx * sizeof(double),
+      CU(cudaMemcpy2DAsync(dA, (size_t)lda * sizeof(double), X_ts, (size_t)ldx * sizeof(double),
                            (size_t)n_ts * sizeof(double), nvar, cudaMemcpyHostToDevice, h->st));
-      h->launches += launch_predict(g, h->b, n_ts, dA, n_ts, first, thin, S, dLV, chunk, dAcc, dP, h->st);
+      CU(cudaEventCreate(&e0));
+      CU(cudaEventCreate(&e1));
+      CU(cudaEventRecord(e0, h->st));
+      h->launches += launch_predict(g, h->b, n_ts, dA, lda, first, thin, S, dLV, chunk, dAcc, dP, h->st);
+      CU(cudaEventRecord(e1, h->st));
       CU(cudaStreamSynchronize(h->st));
+      float ms = 0;
+      CU(cudaEventElapsedTime(&ms, e0, e1));
+      h->last_predict_ms = ms;
+      h->last_predict_flops = 2.0 * n_ts * (double)nvar * (double)K * S;
       CU(cudaGetLastError());
       CU(cudaMemcpy(probs, dP, sizeof(double) * (size_t)n_ts * (K + 1), cudaMemcpyDeviceToHost));
     } catch (...) {
@@ -1286,6 +1302,47 @@ int htlr_cuda_profile_get(htlr_handle* h, htlr_profile* out, int32_t reset) {
 }
 
 int64_t htlr_cuda_launch_count(const htlr_handle* h) { return h ? h->launches : 0; }
+
+int htlr_cuda_predict_stats(const htlr_handle* h, double* kernel_ms, double* flops) {
+  if (!h) return HTLR_E_ARG;
+  if (kernel_ms) *kernel_ms = h->last_predict_ms;
+  if (flops) *flops = h->last_predict_flops;
+  return HTLR_OK;
+}
+
+int htlr_cuda_fp64_peak(int32_t device, double* dfma_tflops, double* dmma_tflops) {
+  return guarded(nullptr, [&] {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+      FAIL(HTLR_E_CUDA, "no CUDA device visible: this library has no CPU fallback");
+    CU(cudaSetDevice(device));
+    const DevInfo& dev = dev_info(device);
+    double* sink = nullptr;
+    CU(cudaMalloc((void**)&sink, sizeof(double)));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    const int iters = 20000;
+    for (int mode = 0; mode < 2; ++mode) {
+      launch_fp64_peak(dev.sm_count, 200, mode, sink, 0);   // warm-up
+      CU(cudaEventRecord(e0, 0));
+      launch_fp64_peak(dev.sm_count, iters, mode, sink, 0);
+      CU(cudaEventRecord(e1, 0));
+      CU(cudaEventSynchronize(e1));
+      float ms = 0;
+      CU(cudaEventElapsedTime(&ms, e0, e1));
+      const double threads = (double)dev.sm_count * 8 * 256;
+      // per thread and round: 16 FMAs (2 flops each) / 8 warp-wide DMMAs (8x8x4 FMAs per warp = 16 flops per lane)
+      const double flops = threads * iters * (mode ? 8 * 16.0 : 16 * 2.0);
+      double* out = mode ? dmma_tflops : dfma_tflops;
+      if (out) *out = flops / (ms * 1e-3) / 1e12;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    CU(cudaGetLastError());
+  });
+}
 
 int64_t htlr_cuda_ars_table_full(htlr_handle* h) {
   if (!h) return -1;

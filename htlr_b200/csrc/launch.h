@@ -126,6 +126,8 @@ void launch_trace_summary(const Geom& g, const Bufs& b, int first, int last, int
 int launch_predict(const Geom& g, const Bufs& b, int M, const double* A, int64_t lda, int first, int thin, int S,
                    double* LV, int chunk, double* accum, double* probs, cudaStream_t st);
 
+void launch_fp64_peak(int sm_count, int iters, int use_dmma, double* sink, cudaStream_t st);
+
 // traj_kernel.cu
 bool fused_plan(const Geom& g, int smem_optin_bytes, int cl, FusedGeom* out);
 int fused_cluster_size(const Geom& g, int smem_optin_bytes);

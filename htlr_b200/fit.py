@@ -55,12 +55,17 @@ class Sampler:
 
     def __init__(self, p, K, n, X, ymat, ybase, ptype, alpha, s, eta, iters_rmc, iters_h, thin, leap_L, leap_L_h,
                  leap_step, hmc_sgmcut, deltas, sigmasbt, keep_warmup_hist=False, silence=1, legacy=False, *,
-                 device=0, rng_mode=RNG_DEVICE, seed=0, algo=0, use_graph=True, nccl_comm=None,
+                 device=0, rng_mode=RNG_DEVICE, seed=None, algo=0, use_graph=True, nccl_comm=None,
                  ars_inject_width=0, device_ptrs=None):
         """`device_ptrs=(X_ptr, ldx, ymat_ptr, ybase_ptr)`: the three n-sized inputs already live in device
         memory (column-major FP64 with even leading dimension ldx; ybase int64) and `X`, `ymat`, `ybase` are
         ignored — used for tall data generated on the GPU (htlr_cfg.x_on_device)."""
         L = _lib.lib()
+        if seed is None:
+            # the reference draws from R's global stream: two fits that do not fix a seed differ. Same here: a fresh
+            # key per sampler unless one is given (kept in self.seed and in the fit's "mc.param")
+            seed = int(np.random.SeedSequence().entropy) & ((1 << 64) - 1)
+        self.seed = int(seed)
         if isinstance(ptype, str):
             if ptype not in PTYPES:
                 raise HtlrCudaError(1, f"Unsupported prior type {ptype}")
@@ -183,7 +188,8 @@ class Sampler:
         out = {"p": self.p, "n": self.n, "K": self.K,
                "mc.param": {"iter.rmc": self.iters_rmc, "iter.warm": self.iters_h, "thin": self.thin,
                             "leap": self.leap_L, "leap.warm": self.leap_L_h, "leap.step": self.leap_step,
-                            "sgmsq.cut": sg * sg if sg > 0 else sg, "DDNloglike": ddn}}
+                            "sgmsq.cut": sg * sg if sg > 0 else sg, "DDNloglike": ddn},
+               "cuda.seed": self.seed}
         out.update(o)
         return out
 
@@ -209,6 +215,13 @@ class Sampler:
         probs = np.zeros((n_ts, self.C), order="F")
         self._check(_lib.lib().htlr_cuda_predict(self.h, _ptr(X_ts), n_ts, n_ts, first, last, thin, _ptr(probs)))
         return probs
+
+    def predict_stats(self):
+        """(kernel milliseconds, FP64 flops) of the last predict() call."""
+        ms, fl = ctypes.c_double(), ctypes.c_double()
+        bd = lambda x: ctypes.cast(ctypes.byref(x), c_dp)
+        self._check(_lib.lib().htlr_cuda_predict_stats(self.h, bd(ms), bd(fl)))
+        return ms.value, fl.value
 
     # -- deterministic pieces (parity hooks)
     def eval(self, iup, deltas):
@@ -275,7 +288,7 @@ class Sampler:
 
 def htlr_fit_helper(p, K, n, X, ymat, ybase, ptype, alpha, s, eta, iters_rmc, iters_h, thin, leap_L, leap_L_h,
                     leap_step, hmc_sgmcut, deltas, sigmasbt, keep_warmup_hist, silence, legacy, *, device=0,
-                    seed=0, progress=None, **kw):
+                    seed=None, progress=None, **kw):
     """Drop-in for the reference's `htlr_fit_helper` (src/main.cpp:7-25): Fit ctor, StartSampling, OutputR.
 
     Pipelined like htlr_cuda_fit: units of 8 iterations, up to 64 in flight, each unit's trace slices downloaded
@@ -332,6 +345,16 @@ def ars_sample(kind, var_deltas, K, alpha, log_aw, uniforms=None, seed=0, step=0
     if rc:
         raise HtlrCudaError(rc, L.htlr_cuda_last_error(None).decode())
     return {"x": x, "n_unif": nu, "n_eval": ne, "status": st}
+
+
+def fp64_peak(device=0):
+    """Measured FP64 peaks of the device in TFLOP/s: {"dfma": vector pipe, "dmma": tensor-core m8n8k4}."""
+    a, b = ctypes.c_double(), ctypes.c_double()
+    bd = lambda x: ctypes.cast(ctypes.byref(x), c_dp)
+    rc = _lib.lib().htlr_cuda_fp64_peak(device, bd(a), bd(b))
+    if rc:
+        raise HtlrCudaError(rc, _lib.lib().htlr_cuda_last_error(None).decode())
+    return {"dfma": a.value, "dmma": b.value}
 
 
 def rng_dump(seed, purpose, step, n_a, n_b, kind, shape=1.0, device=0):

@@ -241,6 +241,12 @@ void* htlr_cuda_stream(htlr_handle* h);                 /* cudaStream_t all work
 int htlr_cuda_profile_enable(htlr_handle* h, int32_t on); /* on: eager launches + per-kernel CUDA events */
 int htlr_cuda_profile_get(htlr_handle* h, htlr_profile* out, int32_t reset);
 int64_t htlr_cuda_launch_count(const htlr_handle* h);   /* kernels launched by this handle so far */
+/* Device time (CUDA events around the kernels, copies excluded) and FP64 flops (2 n_ts (p+1) K S) of the last
+ * htlr_cuda_predict call of this handle. */
+int htlr_cuda_predict_stats(const htlr_handle* h, double* kernel_ms, double* flops);
+/* Measured FP64 peaks of a device in TFLOP/s: independent DFMA chains (vector pipe) and independent m8n8k4 DMMA chains
+ * (the path htlr_cuda_predict's contraction runs on); the roofline denominators of the prediction block of bench.py. */
+int htlr_cuda_fp64_peak(int32_t device, double* dfma_tflops, double* dmma_tflops);
 /* Adaptive rejection sampling (ghs / neg variances, logw): the reference's hull table holds max_nhull = 1000 tangents
  * and silently stops tightening the envelope once it is full (src/ars.cpp:26, src/ars.h:59-62); the device engine does
  * the same with 16 tangents per feature (32 for logw). The draws stay exact either way. This returns how many draws of

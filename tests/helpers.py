@@ -62,6 +62,21 @@ def streams(args, seed=0, ars_width=0):
     return out
 
 
+def comp_lsl_np(lv):
+    """comp_lsl (src/utils.cpp:59-70 via log_sum_exp): log-sum-exp over cbind(0, lv) along axis 1, max-shifted. Pinned
+    to the reference's own output for the golden matrix (tests/golden/util_vectors.npz, htlr_ref_comp_lsl) by
+    tests/test_oracle_pinned.py::test_posterior_restatements_are_pinned_to_reference_vectors."""
+    full = np.concatenate([np.zeros_like(lv[:, :1]), lv], axis=1)
+    m = full.max(axis=1, keepdims=True)
+    return np.log(np.exp(full - m).sum(axis=1, keepdims=True)) + m
+
+
+def comp_sdb_np(deltas):
+    """comp_sdb (R/util.r:91-105): sqrt(comp_vardeltas(deltas) / C); comp_vardeltas pinned like comp_lsl_np."""
+    C = deltas.shape[1] + 1
+    return np.sqrt(synth.comp_vardeltas(deltas) / C)
+
+
 def posterior_summary(fit, burn=None, thin=1, cut=0.1):
     """numpy restatement of the reference's posterior summaries for a fit dict (OutputR names):
     get_sample_indice / htlr_sdb / nzero_idx (R/mccoef.r:104-156), summary(method = mean) (R/mccoef.r:38-62),
@@ -73,9 +88,7 @@ def posterior_summary(fit, burn=None, thin=1, cut=0.1):
     n_burn = int(np.floor(iter_rmc * 0.2)) if burn is None else burn
     used = np.arange(n_warm + n_burn + 1, H + 1, thin)          # 1-based slice numbers, ignore.first = TRUE
     mean = mcd[:, :, used - 1].mean(axis=2)
-    d = mean[1:]
-    C = d.shape[1] + 1
-    sdb = np.sqrt(synth.comp_vardeltas(d) / C)
+    sdb = comp_sdb_np(mean[1:])
     return {"used": used, "mean_deltas": mean, "sdb": sdb, "nzero_idx": np.nonzero(sdb > cut * sdb.max())[0] + 1}
 
 
@@ -88,8 +101,6 @@ def predict_reference(fit, X_ts, burn=None, thin=1):
     used = np.arange(H - iter_rmc + n_burn + 0, H + 1, thin)     # 1-based, ignore.first = FALSE
     used = used[used >= 1]
     lv = np.einsum("ij,jks->iks", X_ts, mcd[:, :, used - 1])     # n_ts x K x S
-    full = np.concatenate([np.zeros_like(lv[:, :1]), lv], axis=1)
-    m = full.max(axis=1, keepdims=True)
-    lsl = np.log(np.exp(full - m).sum(axis=1, keepdims=True)) + m
+    lsl = comp_lsl_np(lv)                                        # n_ts x 1 x S
     probs = np.exp(lv - lsl).mean(axis=2)
     return np.c_[np.maximum(0.0, 1.0 - probs.sum(axis=1)), probs]

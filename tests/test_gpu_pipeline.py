@@ -88,3 +88,15 @@ def test_pipelined_helper_with_thinning_and_the_other_priors(over):
     out = htlr_b200.htlr_fit_helper(**args, seed=33)
     for k in TRACE:
         assert np.array_equal(out[k], ref[k]), k
+
+
+def test_unseeded_fits_differ_and_the_reported_seed_reproduces_them():
+    """the reference draws from R's global stream, so two fits without set.seed() differ; a default seed
+    of 0 silently made them identical. Now a fresh key per sampler, reported in the fit."""
+    import htlr_b200
+    args = problem(80, 60, 3, seed=2, iters_h=3, iters_rmc=5, leap_L=6, leap_L_h=2)
+    a = htlr_b200.htlr_fit_helper(**args)
+    b = htlr_b200.htlr_fit_helper(**args)
+    assert a["cuda.seed"] != b["cuda.seed"] and not np.array_equal(a["mcdeltas"], b["mcdeltas"])
+    c = htlr_b200.htlr_fit_helper(**args, seed=a["cuda.seed"])
+    assert np.array_equal(a["mcdeltas"], c["mcdeltas"]) and np.array_equal(a["mcsigmasbt"], c["mcsigmasbt"])
