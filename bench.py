@@ -424,37 +424,25 @@ def measure_chains(torch, steps, warmup, nch, dist, rank, world, local, cpu_base
 
 
 def make_tall_on_device(torch, n_total, p, C, rank, world, seed):
-    """gendata_MLR law (R/gendata.r:26-46) for this rank's row block, generated on the GPU (16 GB of X at
-    full size never exists on the host). Coefficients come from the common seed, rows from seed + 1 + rank."""
+    """gendata_MLR's law (R/gendata.r:26-46) for this rank's row block, generated on the GPU by the library's own
+    generator (htlr_cuda_gendata_mlr: keyed by the GLOBAL row, so the ranks' blocks are slices of ONE data set whatever
+    the sharding; 16 GB of X at full size never exists on the host)."""
+    import htlr_b200
     from htlr_b200 import shard
     lo, hi = shard.row_range(n_total, rank, world)
     nl = hi - lo
     ld = (nl + 15) // 16 * 16
     dev = torch.device("cuda", torch.cuda.current_device())
-    gc = torch.Generator(device=dev); gc.manual_seed(seed)
-    gr = torch.Generator(device=dev); gr.manual_seed(seed + 1 + rank)
-    sig = 1.0 / torch.empty(p, dtype=torch.float64, device=dev).exponential_(1.0, generator=gc)   # 1/Gamma(1, 1)
-    betas = torch.randn(p + 1, C, dtype=torch.float64, device=dev, generator=gc)
-    betas *= torch.cat([torch.zeros(1, dtype=torch.float64, device=dev), sig.sqrt()])[:, None]
     Xt = torch.zeros(p + 1, ld, dtype=torch.float64, device=dev)     # row j = column j of X (column-major n x nvar)
-    Xt[0, :nl] = 1.0
-    lv = betas[0][None, :].repeat(nl, 1)
-    step = max(1, (1 << 27) // ld)
-    for j0 in range(1, p + 1, step):
-        j1 = min(p + 1, j0 + step)
-        blk = torch.randn(j1 - j0, nl, dtype=torch.float64, device=dev, generator=gr)
-        Xt[j0:j1, :nl] = blk
-        lv += blk.T @ betas[j0:j1]          # data generation only (cuBLAS); not part of the measured path
-        del blk
+    ymat = torch.zeros(C - 1, nl, dtype=torch.float64, device=dev)   # [k][i]
+    ybase = torch.zeros(nl, dtype=torch.int64, device=dev)
+    htlr_b200.gendata_mlr_device(nl, p, C, Xt.data_ptr(), ld, ymat.data_ptr(), ybase.data_ptr(), seed=seed, row0=lo,
+                                 device=dev.index)
     # coefficients this heavy-tailed give near-degenerate class probabilities; that is the law, keep it
-    pr = torch.softmax(lv, dim=1)
-    y = torch.multinomial(pr, 1, generator=gr).squeeze(1)
-    if rank == 0:
-        y[:C] = torch.arange(C, device=dev)
-    K = C - 1
-    ymat = (y[None, :] == torch.arange(1, C, device=dev)[:, None]).to(torch.float64).contiguous()   # [k][i]
-    ybase = y.to(torch.int64).contiguous()
-    return dict(Xt=Xt, ld=ld, ymat=ymat, ybase=ybase, n_local=nl, K=K)
+    if rank == 0:   # every class present (R/core.r:90-100 requires two cases per class; the first rows make sure)
+        ybase[:2 * C] = torch.arange(2 * C, device=dev) % C
+        ymat[:, :2 * C] = (ybase[None, :2 * C] == torch.arange(1, C, device=dev)[:, None]).to(torch.float64)
+    return dict(Xt=Xt, ld=ld, ymat=ymat, ybase=ybase, n_local=nl, K=C - 1)
 
 
 def measure_tall(torch, steps, warmup, n_total, dist, rank, world, local, cpu_baseline=True):

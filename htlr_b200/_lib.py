@@ -65,7 +65,7 @@ EXPORTS = [
     "htlr_cuda_collect", "htlr_cuda_release_cache",
     "htlr_cuda_fit", "htlr_cuda_summary", "htlr_cuda_predict", "htlr_cuda_std", "htlr_cuda_eval", "htlr_cuda_trajectory", "htlr_cuda_get_state", "htlr_cuda_ars",
     "htlr_cuda_rng_dump", "htlr_cuda_stream", "htlr_cuda_profile_enable", "htlr_cuda_profile_get",
-    "htlr_cuda_launch_count", "htlr_cuda_ars_table_full", "htlr_cuda_predict_stats", "htlr_cuda_fp64_peak", "htlr_cuda_sync", "htlr_cuda_run_async", "htlr_cuda_nccl_unique_id",
+    "htlr_cuda_gendata_mlr", "htlr_cuda_gendata_fam", "htlr_cuda_launch_count", "htlr_cuda_ars_table_full", "htlr_cuda_predict_stats", "htlr_cuda_fp64_peak", "htlr_cuda_sync", "htlr_cuda_run_async", "htlr_cuda_nccl_unique_id",
     "htlr_cuda_nccl_init", "htlr_cuda_nccl_destroy", "htlr_cuda_last_error", "htlr_cuda_abi_version",
 ]
 
@@ -94,6 +94,13 @@ def lib():
     L.htlr_cuda_stream.argtypes = [ctypes.c_void_p]
     L.htlr_cuda_launch_count.restype = ctypes.c_int64
     L.htlr_cuda_launch_count.argtypes = [ctypes.c_void_p]
+    L.htlr_cuda_gendata_mlr.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_double,
+                                        ctypes.c_double, ctypes.c_uint64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
+                                        ctypes.c_void_p, ctypes.c_void_p, c_dp]
+    L.htlr_cuda_gendata_fam.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, c_dp,
+                                        ctypes.c_int32, ctypes.c_int32, c_dp, ctypes.c_double, ctypes.c_int32,
+                                        ctypes.c_uint64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
+                                        ctypes.c_void_p, ctypes.c_void_p]
     L.htlr_cuda_predict_stats.argtypes = [ctypes.c_void_p, c_dp, c_dp]
     L.htlr_cuda_fp64_peak.argtypes = [ctypes.c_int32, c_dp, c_dp]
     L.htlr_cuda_ars_table_full.restype = ctypes.c_int64

@@ -1261,6 +1261,67 @@ int htlr_cuda_std(int32_t device, int32_t n, int32_t p, const double* A, int64_t
   });
 }
 
+int htlr_cuda_gendata_mlr(int32_t device, int32_t n, int32_t p, int32_t NC, double nu, double w, uint64_t seed,
+                          int64_t row0, double* X, int64_t ldx, double* ymat, int64_t* ybase, double* deltas_true) {
+  return guarded(nullptr, [&] {
+    if (n < 1 || p < 1 || NC < 2 || NC > kMaxK + 1 || !X || !ymat || !ybase || ldx < n || !(nu > 0) || !(w > 0))
+      FAIL(HTLR_E_ARG, "bad arguments for gendata_mlr (2 <= NC <= 17, ldx >= n, device pointers)");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+      FAIL(HTLR_E_CUDA, "no CUDA device visible: this library has no CPU fallback");
+    CU(cudaSetDevice(device));
+    double *betas = nullptr, *part = nullptr;
+    auto cleanup = [&] { cudaFree(betas); cudaFree(part); };
+    try {
+      CU(cudaMalloc((void**)&betas, sizeof(double) * (size_t)(p + 1) * NC));
+      CU(cudaMalloc((void**)&part, sizeof(double) * (size_t)gen_mlr_chunks(p) * NC * n));
+      launch_gen_mlr(n, p, NC, nu, w, seed, row0, X, ldx, ymat, reinterpret_cast<long long*>(ybase), betas, part, 0);
+      CU(cudaDeviceSynchronize());
+      CU(cudaGetLastError());
+      if (deltas_true) {   // deltas = betas[, -1] - betas[, 1]
+        std::vector<double> bh((size_t)(p + 1) * NC);
+        CU(cudaMemcpy(bh.data(), betas, bh.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        for (int k = 0; k < NC - 1; ++k)
+          for (int j = 0; j <= p; ++j)
+            deltas_true[(size_t)k * (p + 1) + j] = bh[(size_t)(k + 1) * (p + 1) + j] - bh[j];
+      }
+    } catch (...) {
+      cleanup();
+      throw;
+    }
+    cleanup();
+  });
+}
+
+int htlr_cuda_gendata_fam(int32_t device, int32_t n, int32_t p, int32_t NC, const double* muj, int32_t pb, int32_t kb,
+                          const double* Ablock, double sd_g, int32_t stdx, uint64_t seed, int64_t row0, double* X,
+                          int64_t ldx, double* ymat, int64_t* ybase) {
+  return guarded(nullptr, [&] {
+    if (n < 1 || p < 1 || NC < 2 || NC > kMaxK + 1 || !muj || !X || !ymat || !ybase || ldx < n || pb < 0 || pb > p ||
+        kb < 0 || kb > pb || (pb > 0 && !Ablock) || !(sd_g >= 0))
+      FAIL(HTLR_E_ARG, "bad arguments for gendata_fam (2 <= NC <= 17, 0 <= kb <= pb <= p, ldx >= n, device pointers)");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+      FAIL(HTLR_E_CUDA, "no CUDA device visible: this library has no CPU fallback");
+    CU(cudaSetDevice(device));
+    double *dmu = nullptr, *dA = nullptr;
+    auto cleanup = [&] { cudaFree(dmu); cudaFree(dA); };
+    try {
+      CU(cudaMalloc((void**)&dmu, sizeof(double) * (size_t)p * NC));
+      CU(cudaMemcpy(dmu, muj, sizeof(double) * (size_t)p * NC, cudaMemcpyHostToDevice));
+      CU(cudaMalloc((void**)&dA, sizeof(double) * (size_t)std::max(1, pb * kb)));
+      if (pb * kb > 0) CU(cudaMemcpy(dA, Ablock, sizeof(double) * (size_t)pb * kb, cudaMemcpyHostToDevice));
+      launch_gen_fam(n, p, NC, pb, kb, dmu, dA, sd_g, stdx, seed, row0, X, ldx, ymat, reinterpret_cast<long long*>(ybase), 0);
+      CU(cudaDeviceSynchronize());
+      CU(cudaGetLastError());
+    } catch (...) {
+      cleanup();
+      throw;
+    }
+    cleanup();
+  });
+}
+
 void* htlr_cuda_stream(htlr_handle* h) { return h ? (void*)h->st : nullptr; }
 
 int htlr_cuda_profile_enable(htlr_handle* h, int32_t on) {

@@ -126,6 +126,13 @@ void launch_trace_summary(const Geom& g, const Bufs& b, int first, int last, int
 int launch_predict(const Geom& g, const Bufs& b, int M, const double* A, int64_t lda, int first, int thin, int S,
                    double* LV, int chunk, double* accum, double* probs, cudaStream_t st);
 
+// gen_kernels.cu: gendata_MLR / gendata_FAM laws on the device (betas: (p+1) x NC scratch/output, part: chunks x NC x n)
+void launch_gen_mlr(int n, int p, int NC, double nu, double w, unsigned long long seed, long long row0, double* X,
+                    int64_t ld, double* ymat, long long* ybase, double* betas, double* part, cudaStream_t st);
+int gen_mlr_chunks(int p);
+void launch_gen_fam(int n, int p, int NC, int pb, int kb, const double* muj, const double* Ab, double sd_g, int stdx,
+                    unsigned long long seed, long long row0, double* X, int64_t ld, double* ymat, long long* ybase,
+                    cudaStream_t st);
 void launch_fp64_peak(int sm_count, int iters, int use_dmma, double* sink, cudaStream_t st);
 
 // traj_kernel.cu

@@ -347,6 +347,30 @@ def ars_sample(kind, var_deltas, K, alpha, log_aw, uniforms=None, seed=0, step=0
     return {"x": x, "n_unif": nu, "n_eval": ne, "status": st}
 
 
+def gendata_mlr_device(n, p, NC, X_ptr, ldx, ymat_ptr, ybase_ptr, nu=2.0, w=1.0, seed=0, row0=0, device=0,
+                       want_deltas=False):
+    """gendata_MLR's law (R/gendata.r:26-46) for rows [row0, row0 + n) of a data set, generated on the GPU into the
+    caller's device buffers (X n x (p+1) col-major with leading dimension ldx, ymat n x (NC-1), ybase int64)."""
+    d = np.zeros((p + 1, NC - 1), order="F") if want_deltas else None
+    rc = _lib.lib().htlr_cuda_gendata_mlr(device, n, p, NC, float(nu), float(w), seed, row0, X_ptr, ldx, ymat_ptr,
+                                          ybase_ptr, _ptr(d))
+    if rc:
+        raise HtlrCudaError(rc, _lib.lib().htlr_cuda_last_error(None).decode())
+    return d
+
+
+def gendata_fam_device(n, muj, Ablock, X_ptr, ldx, ymat_ptr, ybase_ptr, sd_g=0.0, stdx=False, seed=0, row0=0, device=0):
+    """gendata_FAM's law (R/gendata.r:105-113, src/utils.cpp:72-105) with A = I_p + a leading pb x kb block."""
+    muj = _f64(muj, "F")
+    p, NC = muj.shape
+    Ab = _f64(np.atleast_2d(Ablock), "F")
+    pb, kb = Ab.shape
+    rc = _lib.lib().htlr_cuda_gendata_fam(device, n, p, NC, _ptr(muj), pb, kb, _ptr(Ab), float(sd_g), int(stdx), seed,
+                                          row0, X_ptr, ldx, ymat_ptr, ybase_ptr)
+    if rc:
+        raise HtlrCudaError(rc, _lib.lib().htlr_cuda_last_error(None).decode())
+
+
 def fp64_peak(device=0):
     """Measured FP64 peaks of the device in TFLOP/s: {"dfma": vector pipe, "dmma": tensor-core m8n8k4}."""
     a, b = ctypes.c_double(), ctypes.c_double()

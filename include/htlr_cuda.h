@@ -258,6 +258,22 @@ int htlr_cuda_sync(htlr_handle* h);
 /* enqueue n_iters iterations without synchronising or copying stats (bench timed region) */
 int htlr_cuda_run_async(htlr_handle* h, int32_t n_iters);
 
+/* ---- synthetic data on the device: the laws of the reference's generators, written straight into the
+ * layout htlr_cuda_create takes with x_on_device. All array arguments but muj / Ablock / deltas_true are DEVICE
+ * pointers: X n x (p+1) column-major with leading dimension ldx (column 0 = ones), ymat n x (NC-1) column-major
+ * (leading dimension n), ybase n. Variates are keyed by (seed, global row row0 + i, column): any row block of one
+ * data set can be generated on any GPU. 2 <= NC <= 17.
+ * gendata_MLR (R/gendata.r:26-46): X ~ N(0,1), sigmasbt = w / Gamma(nu/2, rate nu/2), betas = N(0,1) * c(0, sqrt(sigmasbt)),
+ *   y ~ categorical(softmax(cbind(1, X) betas)); deltas_true (host, (p+1) x (NC-1), nullable) = betas[, -1] - betas[, 1].
+ * gendata_FAM (R/gendata.r:105-113, src/utils.cpp:72-105): y = rep(1:NC, len = n), X = A z + muj[, y] + sd_g e with
+ *   A = I_p whose leading pb x kb block is Ablock (host, pb x kb column-major; the vignette's factor pattern), muj host
+ *   p x NC column-major; stdx != 0 standardises with the model's means and variances as the reference does. */
+int htlr_cuda_gendata_mlr(int32_t device, int32_t n, int32_t p, int32_t NC, double nu, double w, uint64_t seed,
+                          int64_t row0, double* X, int64_t ldx, double* ymat, int64_t* ybase, double* deltas_true);
+int htlr_cuda_gendata_fam(int32_t device, int32_t n, int32_t p, int32_t NC, const double* muj, int32_t pb, int32_t kb,
+                          const double* Ablock, double sd_g, int32_t stdx, uint64_t seed, int64_t row0, double* X,
+                          int64_t ldx, double* ymat, int64_t* ybase);
+
 /* ---- multi-GPU plumbing (row-sharded X) ---- */
 int htlr_cuda_nccl_unique_id(void* id128 /* 128 bytes */);
 int htlr_cuda_nccl_init(const void* id128, int32_t rank, int32_t world, int32_t device, void** comm);
