@@ -510,7 +510,7 @@ void do_create(const htlr_cfg* cfg, const double* X, int64_t ldx, const double* 
   if (cfg->abi_version != HTLR_CUDA_ABI_VERSION) FAIL(HTLR_E_ARG, "htlr_cfg.abi_version mismatch");
   const htlr_cfg& c = *cfg;
   if (c.p < 1 || c.K < 1 || c.n < 1) FAIL(HTLR_E_ARG, "p, K, n must be positive");
-  if (c.K > kMaxK) FAIL(HTLR_E_ARG, "K > 16 classes-1 is not supported by this build");
+  if (c.K > 4096) FAIL(HTLR_E_ARG, "more than 4097 classes are not supported");
   if (c.ptype < 0 || c.ptype > 2) FAIL(HTLR_E_ARG, "Unsupported prior type");
   if (!(c.iters_rmc > 0 && c.iters_h >= 0 && c.thin > 0 && c.leap_L > 0 && c.leap_L_h > 0))
     FAIL(HTLR_E_ARG, "iters_rmc > 0, iters_h >= 0, thin > 0, leap_L > 0, leap_L_h > 0 required");

@@ -6,7 +6,7 @@
 
 namespace htlr {
 
-constexpr int kMaxK = 16;  // classes - 1 supported by the generic kernels (templated fast paths for K <= 4)
+constexpr int kMaxK = 16;  // classes - 1 the generic kernels hold in registers at a time (more: kMaxK per pass over X)
 
 // Error codes stored in Ctl::err (sticky, first one wins).
 enum DevErr : int {

@@ -140,6 +140,17 @@ __global__ void __launch_bounds__(256) k_predict_accum(int M, int K, int nt, con
                                                         double* __restrict__ accum) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M) return;
+  if (K > kMaxK) {   // many classes: no register arrays, three passes over the classes per sample
+    for (int t = 0; t < nt; ++t) {
+      double m = 0.0;
+      for (int k = 0; k < K; ++k) m = fmax(m, LV[((int64_t)t * K + k) * M + i]);
+      double se = exp(0.0 - m);
+      for (int k = 0; k < K; ++k) se += exp(LV[((int64_t)t * K + k) * M + i] - m);
+      const double lsl = log(se) + m;
+      for (int k = 0; k < K; ++k) accum[(int64_t)k * M + i] += exp(LV[((int64_t)t * K + k) * M + i] - lsl);
+    }
+    return;
+  }
   double a[kMaxK];
   for (int k = 0; k < K; ++k) a[k] = accum[(int64_t)k * M + i];
   for (int t = 0; t < nt; ++t) {

