@@ -498,6 +498,10 @@ def measure_tall(torch, steps, warmup, n_total, dist, rank, world, local, cpu_ba
     # two X sweeps per leapfrog step are inherent when rows are sharded (the gradient of a column needs every rank's
     # rows before the column can move): 2 (L+1) sweeps of this rank's 8 n_local u bytes (+ the detach sweep)
     bound_bytes = 2.0 * (L + 1) * 8.0 * nl * u
+    tt = ncu_traffic("tall_sweeps_200000_rows") if nl == 200000 else None
+    tall_tr = 0.5 * (tt["k_lv_sweep<4>"] + tt["k_grad_sweep<4>"]) if tt else None
+    tall_src = ("profiles/traffic.json (dram__bytes_read.sum per launch, mean of the two sweep kernels at 200000 rows per "
+                "GPU, committed ncu capture; not re-measured in this run)") if tt else "not captured at this shard size"
     it_s = steps / (ms_max * 1e-3)
     line = {"metric": "mcmc_iterations_per_sec", "value": it_s, "unit": "it/s", "n_gpus": world,
             "steps": steps, "warmup": warmup, "ms_per_step": ms_max / steps, "higher_is_better": True,
@@ -512,11 +516,15 @@ def measure_tall(torch, steps, warmup, n_total, dist, rank, world, local, cpu_ba
                     "hmc_reject": float(np.mean(out["mchmcrej"][warmup + 1:warmup + 1 + steps]))},
             "gpu_launches": launches, "clocks": clk,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": None, "traffic_source": "not captured for this workload",
+                         "traffic": tall_tr, "traffic_source": tall_src,
                          "kernel": "k_lv_sweep + k_grad_sweep over this rank's row block",
                          "peak_source": peak_src, "launches_timed": pr["sweep_launches"],
                          "algorithmic_bytes_per_launch": pr["sweep_bytes"] / max(pr["sweep_launches"], 1),
                          "sweep_share_of_step": pr["sweep_ms"] / max(pr["total_ms"], 1e-9),
+                         # NCCL all-reduce of the (p+1) x K gradient (+ log-likelihood), once per gradient evaluation:
+                         # CUDA events around the call on the library's stream, same eager pass as the sweep times
+                         "allreduce_share_of_step": pr["allreduce_ms"] / max(pr["total_ms"], 1e-9),
+                         "allreduce_us_per_call": 1e3 * pr["allreduce_ms"] / max(psteps * (L + 1), 1) if world > 1 else None,
                          "two_sweep_bound": {"bytes_per_iteration_per_rank": bound_bytes,
                                              "it_s_at_measured_peak": peak * 1e9 / bound_bytes,
                                              "frac_iteration": it_s * bound_bytes / 1e9 / peak}}}

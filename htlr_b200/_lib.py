@@ -14,7 +14,7 @@ c_dp = ctypes.POINTER(ctypes.c_double)
 c_ip = ctypes.POINTER(ctypes.c_int32)
 c_lp = ctypes.POINTER(ctypes.c_int64)
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class HtlrCfg(ctypes.Structure):
@@ -53,7 +53,7 @@ class HtlrProfile(ctypes.Structure):
                 ("kernel_launches", ctypes.c_int64), ("sigma_ms", ctypes.c_double),
                 ("fused_sweep_ms", ctypes.c_double), ("fused_barrier_ms", ctypes.c_double),
                 ("fused_rowphase_ms", ctypes.c_double), ("small_kernel_trajectories", ctypes.c_double),
-                ("timeline_us", ctypes.c_double * 12)]
+                ("timeline_us", ctypes.c_double * 12), ("allreduce_ms", ctypes.c_double)]
 
 
 TICK_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(HtlrIterStats),

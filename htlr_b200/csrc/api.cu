@@ -191,7 +191,7 @@ ChunkCache& chunk_cache() {
 
 struct EventPair {
   cudaEvent_t a, b;
-  int kind;  // 0 sweep, 1 step total, 2 sigma
+  int kind;  // 0 sweep, 1 step total, 2 sigma, 3 all-reduce
 };
 
 }  // namespace
@@ -291,6 +291,7 @@ void prof_drain(htlr_handle* h) {
     CU(cudaEventElapsedTime(&ms, h->ev_pool[i].a, h->ev_pool[i].b));
     if (h->ev_pool[i].kind == 0) { h->prof.sweep_ms += ms; h->prof.sweep_launches += 1; }
     else if (h->ev_pool[i].kind == 1) h->prof.total_ms += ms;
+    else if (h->ev_pool[i].kind == 3) h->prof.allreduce_ms += ms;
     else h->prof.sigma_ms += ms;
   }
   h->ev_used = 0;
@@ -334,6 +335,7 @@ int enqueue_step(htlr_handle* h, int L, bool until_energy_only = false) {
     if (h->sharded) {
       launch_gsum(g, b, d_u, b.g, st);
       ++nk;
+      ProfScope pa(h, 3);
       NC(nccl_need().AllReduce(b.g, b.g, (size_t)g.nvar * g.K + 1, ncclDouble, ncclSum, h->comm, st));
     }
     launch_post(g, b, s, L, h->sharded ? 1 : 0, st);

@@ -272,7 +272,8 @@ class Sampler:
         self._check(_lib.lib().htlr_cuda_profile_get(self.h, ctypes.byref(pr), int(reset)))
         out = {k: getattr(pr, k) for k in ("sweep_ms", "sweep_bytes", "sweep_launches", "total_ms",
                                            "kernel_launches", "sigma_ms", "fused_sweep_ms",
-                                           "fused_barrier_ms", "fused_rowphase_ms", "small_kernel_trajectories")}
+                                           "fused_barrier_ms", "fused_rowphase_ms", "small_kernel_trajectories",
+                                           "allreduce_ms")}
         out["timeline_us"] = list(pr.timeline_us)
         return out
 

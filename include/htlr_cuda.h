@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define HTLR_CUDA_ABI_VERSION 1
+#define HTLR_CUDA_ABI_VERSION 2
 
 enum { HTLR_OK = 0, HTLR_E_ARG = 1, HTLR_E_CUDA = 2, HTLR_E_NCCL = 3, HTLR_E_SAMPLER = 4, HTLR_E_STATE = 5 };
 
@@ -132,6 +132,7 @@ typedef struct htlr_profile {
    * sweep, 3 softmax, 4 single-block trajectory, 5 cluster-mode trajectory, 6 grid-mode trajectory, 7 energy,
    * 8 tail */
   double timeline_us[12];
+  double allreduce_ms;    /* row-sharded X: total time of the NCCL all-reduces of the gradient (ABI version 2) */
 } htlr_profile;
 
 /* Replaces `Fit::Fit` + `Fit::Initialize` (gibbs.cpp:4-50, 519-530).

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), n
     assert sorted(htlr_b200._lib.EXPORTS) == names
-    assert lib.htlr_cuda_abi_version() == 1
+    assert lib.htlr_cuda_abi_version() == htlr_b200._lib.ABI_VERSION == 2
 
 
 def test_cfg_struct_layout_matches_header():
