@@ -33,8 +33,8 @@ def test_cfg_struct_layout_matches_header():
     assert ctypes.sizeof(htlr_b200._lib.HtlrCfg) == 144
     assert htlr_b200._lib.HtlrCfg.seed.offset == 112 and htlr_b200._lib.HtlrCfg.nccl_comm.offset == 128
     assert ctypes.sizeof(htlr_b200._lib.HtlrIterStats) == 32
-    # htlr_profile: 10 eight-byte scalars + timeline_us[12]
-    assert ctypes.sizeof(htlr_b200._lib.HtlrProfile) == 8 * 22
+    # htlr_profile: 10 eight-byte scalars + timeline_us[12] + allreduce_ms
+    assert ctypes.sizeof(htlr_b200._lib.HtlrProfile) == 8 * 23
     assert htlr_b200._lib.HtlrProfile.timeline_us.offset == 80
 
 
