@@ -14,8 +14,9 @@ for i, h in enumerate(hdr):
         print(f"  {h} = {vals[i]} {units[i]}")
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
-h = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
-hdr = rows[h]; data = [r for r in rows[h + 1:] if len(r) == len(hdr)]
+hs = [i for i, r in enumerate(rows) if r and r[0] == "Address"]   # one header row per profiled launch: the first one
+h = hs[0]
+hdr = rows[h]; data = [r for r in rows[h + 1:(hs[1] if len(hs) > 1 else len(rows))] if len(r) == len(hdr)]
 ci = {x: i for i, x in enumerate(hdr)}
 stalls = [x for x in hdr if x.startswith("stall_") and "Not Issued" not in x]
 tot = sum(int(r[ci["# Samples"]]) for r in data)
