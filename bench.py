@@ -726,7 +726,7 @@ def main():
     if a.workload == "C_full" and not a.no_extra_blocks:
         if world > 1:
             blocks["sharded_parity"] = sharded_parity(torch, dist, rank, world, local)
-        e_steps = max(3, min(a.steps, 5))
+        e_steps = max(5, min(20, 3 * world))   # an iteration shrinks with the shard: keep the timed region near a second
         blocks["E_row_sharded"] = measure_tall(torch, e_steps, 3, a.n_total, dist, rank, world, local,
                                                cpu_baseline=(world == 1 and not a.no_cpu_baseline))
         blocks["D_chains"] = measure_chains(torch, max(a.steps, 300), a.warmup, a.chains_per_gpu, dist, rank, world, local,
