@@ -11,7 +11,7 @@
 //                                     target eval + insert, accept test
 //   piece helpers   ars.cpp:424-462   logint_elin, interc
 // Layout differs (array of hull records, uniform source object) — arithmetic and branch order do not.
-// Validated bit-for-bit against the reference ars.cpp compiled verbatim (oracle/_ref, tests/test_ars_oracle.py).
+// Validated bit-for-bit against the reference ars.cpp compiled verbatim (oracle/_ref, tests/test_oracle_pinned.py).
 #pragma once
 #include <cmath>
 #include <limits>
