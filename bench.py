@@ -486,8 +486,18 @@ def measure_tall(torch, steps, warmup, n_total, dist, rank, world, local, cpu_ba
     del d
     torch.cuda.empty_cache()
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    same = None
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        # every rank must hold the same trace bit for bit (replicated state, identical keys): checked here at the full
+        # shard size on the recorded log-likelihoods, restricted-set sizes, accept history and the last coefficient slice
+        flat = np.concatenate([np.ravel(out[k]) for k in ("mcloglike", "mcuvar", "mchmcrej")] +
+                              [np.ravel(out["mcdeltas"][:, :, -1])])
+        t0 = torch.from_numpy(flat.copy()).cuda()
+        dist.broadcast(t0, src=0)
+        ok = torch.tensor([1.0 if np.array_equal(t0.cpu().numpy(), flat) else 0.0], device="cuda", dtype=torch.float64)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        same = bool(float(ok[0]) == 1.0)
     ms_max = float(t[0])
     if rank != 0:
         return None
@@ -513,7 +523,9 @@ def measure_tall(torch, steps, warmup, n_total, dist, rank, world, local, cpu_ba
                                    f"{p + 1}x{K} gradient partials + log-likelihood per gradient evaluation"
                     if world > 1 else "1 GPU holds all rows",
                     "algorithm": "two-sweep (lv sweep + gradient sweep per leapfrog step)", "mean_nuvar": u,
-                    "hmc_reject": float(np.mean(out["mchmcrej"][warmup + 1:warmup + 1 + steps]))},
+                    "hmc_reject": float(np.mean(out["mchmcrej"][warmup + 1:warmup + 1 + steps])),
+                    "all_ranks_bit_identical": same,
+                    "loglike_first_last": [float(out["mcloglike"][1]), float(out["mcloglike"][-1])]},
             "gpu_launches": launches, "clocks": clk,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": tall_tr, "traffic_source": tall_src,
