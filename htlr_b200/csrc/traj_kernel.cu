@@ -276,7 +276,16 @@ __global__ void __launch_bounds__(kFT, 1) k_traj(Geom g, Bufs b, FusedGeom fg, i
       const int nc = min(TC, ncols - e0);
       if (lane == 0) mbar_expect_tx(&gfull[ld_stage], col_bytes * (uint32_t)nc);
       __syncwarp();
-      if (lane < nc)
+      // neighbouring columns of a dense X (all features in the restricted set, no padding between columns) are one
+      // contiguous run in memory and in the stage: one copy instead of TC
+      bool run = TC > 1 && g.ld == (int64_t)n_e;
+#pragma unroll
+      for (int c = 1; c < TC; ++c) run = run && (c >= nc || cidx[e0 + c] == cidx[e0] + c);
+      if (run) {
+        if (lane == 0)
+          bulk_g2s(gring + (size_t)ld_stage * TC * n_e, b.X + (int64_t)cidx[e0] * g.ld, col_bytes * (uint32_t)nc,
+                   &gfull[ld_stage]);
+      } else if (lane < nc)
         bulk_g2s(gring + ((size_t)ld_stage * TC + lane) * n_e, b.X + (int64_t)cidx[e0 + lane] * g.ld, col_bytes,
                  &gfull[ld_stage]);
     }
