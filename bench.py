@@ -525,7 +525,7 @@ def measure_tall(torch, steps, warmup, n_total, dist, rank, world, local, cpu_ba
                     "algorithm": "two-sweep (lv sweep + gradient sweep per leapfrog step)", "mean_nuvar": u,
                     "hmc_reject": float(np.mean(out["mchmcrej"][warmup + 1:warmup + 1 + steps])),
                     "all_ranks_bit_identical": same,
-                    "loglike_first_last": [float(out["mcloglike"][1]), float(out["mcloglike"][-1])]},
+                    "loglike_first_last": [float(np.ravel(out["mcloglike"])[1]), float(np.ravel(out["mcloglike"])[-1])]},
             "gpu_launches": launches, "clocks": clk,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": tall_tr, "traffic_source": tall_src,

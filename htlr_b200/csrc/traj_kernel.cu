@@ -125,13 +125,17 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
   return r;
 }
-__device__ __forceinline__ double ld_dsmem(uint32_t addr) {
-  double v;
-  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
-  return v;
+// Asynchronous stores into another block's shared memory that count themselves in on a transaction barrier of the
+// RECEIVING block (addresses already mapped with mapa): the data and the signal travel together, so a cluster-mode
+// exchange needs no fence and no cluster barrier. (barrier.cluster.arrive.release costs a MEMBAR.ALL.GPU, an L2 round
+// trip, for data that never leaves shared memory: 0.35 us per barrier, two per leapfrog step.)
+__device__ __forceinline__ void st_async_f64(uint32_t addr, double v, uint32_t mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f64 [%0], %1, [%2];"
+               ::"r"(addr), "d"(v), "r"(mbar) : "memory");
 }
-__device__ __forceinline__ void st_dsmem(uint32_t addr, double v) {
-  asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+__device__ __forceinline__ void st_async_2f64(uint32_t addr, double v0, double v1, uint32_t mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1, %2}, [%3];"
+               ::"r"(addr), "d"(v0), "d"(v1), "r"(mbar) : "memory");
 }
 __device__ __forceinline__ long long clk() {
   long long t;
@@ -168,11 +172,12 @@ __global__ void __launch_bounds__(kFT, 1) k_traj(Geom g, Bufs b, FusedGeom fg, i
   double* wsum = dl + ((fg.rpc * KT + 1) & ~1);                              // [kCW][rpc*KT] per-warp sums of the partials (grid mode)
   double* rowc = wsum + (CL ? 0 : (size_t)kCW * fg.rpc * KT);                // [rpc][2*KT+2] running lv, ymat, label
   double* cst = rowc + (size_t)fg.rpc * (2 * KT + 2);                        // [ncmax][CS]
-  double* lp_own = cst + (((size_t)fg.ncmax * CS + 1) & ~(size_t)1);         // cluster mode: own lv partial [KT][n_e]
-  double* Rs = lp_own + (CL ? (size_t)KT * n_e : 0);                         // cluster mode: residual copy [KT][n_e]
+  double* prcv = cst + (((size_t)fg.ncmax * CS + 1) & ~(size_t)1);           // cluster mode: lv partials RECEIVED for this block's rows [cl][KT][rpc]
+  double* Rs = prcv + (CL ? (size_t)fg.cl * KT * fg.rpc : 0);                // cluster mode: residual copy [KT][n_e]
   uint64_t* bars = reinterpret_cast<uint64_t*>(Rs + (CL ? (size_t)KT * n_e : 0));
   uint64_t* full = bars;                  // [NG*SG]  TMA -> group
-  int* cidx = reinterpret_cast<int*>(full + NG * SG);    // [ncmax] X column of each owned restricted-set position
+  uint64_t* xbar = full + NG * SG;        // [2]      cluster mode: partials received, residuals received
+  int* cidx = reinterpret_cast<int*>(xbar + 2);          // [ncmax] X column of each owned restricted-set position
 
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const unsigned G = gridDim.x;
@@ -206,6 +211,7 @@ __global__ void __launch_bounds__(kFT, 1) k_traj(Geom g, Bufs b, FusedGeom fg, i
 
   if (tid == 0) {
     for (int i = 0; i < NG * SG; ++i) mbar_init(&full[i], 1);
+    if (CL) { mbar_init(&xbar[0], 1); mbar_init(&xbar[1], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     if (cta == 0) ctl->cols_swept += (unsigned long long)u * (unsigned long long)(L + 1);
   }
@@ -241,6 +247,16 @@ __global__ void __launch_bounds__(kFT, 1) k_traj(Geom g, Bufs b, FusedGeom fg, i
     }
   }
   __syncthreads();
+  // Cluster mode exchanges the lv partials and the residual by asynchronous stores that complete transaction barriers of
+  // the receiving block (xbar[0]: partials of this block's rows from every block, xbar[1]: the residual of every row):
+  // bytes expected per leapfrog step, armed one phase ahead by thread 0. No cluster barrier inside the trajectory; this
+  // one makes every block's barriers (and its residual copy) exist before anybody stores into them.
+  const int xrows = CL ? max(0, min(n_e, (cta + 1) * fg.rpc) - cta * fg.rpc) : 0;   // rows of this block's slice, pad row included
+  const uint32_t xbytes0 = (uint32_t)(gact * xrows * KT) * 8u, xbytes1 = (uint32_t)(n * KT) * 8u;
+  if (CL) {
+    if (tid == 0) { mbar_expect_tx(&xbar[0], xbytes0); mbar_expect_tx(&xbar[1], xbytes1); }
+    cluster_barrier();
+  }
 
   const int ct = tid;
   const int grp = w / GW, wg = w % GW;
@@ -325,6 +341,15 @@ __global__ void __launch_bounds__(kFT, 1) k_traj(Geom g, Bufs b, FusedGeom fg, i
   const bool vwriter = (lane & (32 / VP - 1)) == 0;
   for (int s = 0; s <= L; ++s) {
     if (timer) tk0 = clk();
+    if (CL && s >= 1) {
+      // the residual of step s - 1's softmax has arrived from every row's owner; thread 0 arms the next phase (it cannot
+      // complete before this block has sent the partials of step s, i.e. before all its threads are past this wait)
+      // (the block barrier orders what the cluster barrier at the end of a step used to order inside the block: the
+      // prior-gradient terms and the row state written during the row phase)
+      mbar_wait(&xbar[1], (uint32_t)((s - 1) & 1));
+      if (tid == 0) mbar_expect_tx(&xbar[1], xbytes1);
+      named_bar(kBarAll, kFT);
+    }
     // residual rows of this thread into registers (published by the previous softmax phase)
 #pragma unroll
     for (int m = 0; m < NRP; ++m) {
@@ -543,15 +568,25 @@ __global__ void __launch_bounds__(kFT, 1) k_traj(Geom g, Bufs b, FusedGeom fg, i
 #pragma unroll
       for (int m = 0; m < NRP; ++m) {
         if (rval[m]) {
+          // cluster mode: the pair goes to the block that owns its rows. rpc is even there (fused_plan), so a pair has
+          // one owner and a 16-byte aligned slot in [source block][class][row of the owner's slice]
+          const int owner = CL ? roff[m] / fg.rpc : 0;
+          const uint32_t pdst = CL ? map_to_cta(smem_u32(prcv) + (uint32_t)((cta * KT) * fg.rpc + roff[m] - owner * fg.rpc) * 8u,
+                                                (uint32_t)owner) : 0u;
+          const uint32_t pbar = CL ? map_to_cta(smem_u32(&xbar[0]), (uint32_t)owner) : 0u;
 #pragma unroll
           for (int k = 0; k < KT; ++k) {
-            double* o = CL ? lp_own + k * n_e + roff[m] : b.lvpart + ((int64_t)cta * KT + k) * n_s + roff[m];
-            *reinterpret_cast<double2*>(o) = make_double2(la[m][0][k], la[m][1][k]);
+            if (CL) {
+              st_async_2f64(pdst + (uint32_t)(k * fg.rpc) * 8u, la[m][0][k], la[m][1][k], pbar);
+            } else {
+              double* o = b.lvpart + ((int64_t)cta * KT + k) * n_s + roff[m];
+              *reinterpret_cast<double2*>(o) = make_double2(la[m][0][k], la[m][1][k]);
+            }
           }
         }
       }
     }
-    sync_all();
+    if (!CL) sync_all();
     if (timer) { const long long t = clk(); atomicAdd(&ctl->ph_cycles[1], (unsigned long long)(t - tk0)); tk0 = t; }
 
     // ---- sum the partials in block order, softmax, residual, log-likelihood (rows split over all blocks)
@@ -578,17 +613,22 @@ __global__ void __launch_bounds__(kFT, 1) k_traj(Geom g, Bufs b, FusedGeom fg, i
       double lc = 0.0;   // by_class: this lane's linear predictor (class 0: 0)
       // the partials of one (row, class) item of the cluster's blocks, added in block order
       auto gather = [&](int ii, int k) {
-        const uint32_t base = smem_u32(lp_own) + (uint32_t)(k * n_e + row0 + ii) * 8u;
+        const double* src = prcv + k * fg.rpc + ii;   // [source block][class][row]: received, local
         double pv[kClMax];
 #pragma unroll
-        for (int qq = 0; qq < kClMax; ++qq) pv[qq] = (qq < gact) ? ld_dsmem(map_to_cta(base, (uint32_t)qq)) : 0.0;
+        for (int qq = 0; qq < kClMax; ++qq) pv[qq] = (qq < gact) ? src[qq * KT * fg.rpc] : 0.0;
         double a = pv[0];
 #pragma unroll
         for (int qq = 1; qq < kClMax; ++qq) a += pv[qq];
         return rowc[(size_t)ii * (2 * KT + 2) + k] + a;
       };
       if (CL) {
-        // the partials sit in the owners' shared memory: every load of an item is issued before the first add
+        // the partials of this block's rows have arrived from every block that owns columns; thread 0 arms the next
+        // phase (it cannot complete before this block's residuals of this step are out, i.e. after every wait here)
+        if (xrows > 0) {
+          mbar_wait(&xbar[0], (uint32_t)(s & 1));
+          if (tid == 0) mbar_expect_tx(&xbar[0], xbytes0);
+        }
         if (by_class) {
           if (chave && cc >= 1) lc = gather(crow, cc - 1);
         } else if (KT == 1) {
@@ -661,6 +701,15 @@ __global__ void __launch_bounds__(kFT, 1) k_traj(Geom g, Bufs b, FusedGeom fg, i
           for (int e = ct - base; e < ncols; e += kCT - base) prior_gradient(e);
       }
       double ll = 0;
+      // cluster mode: the new residual of row i, class k into every block's copy, counted in on the receivers' barriers
+      // (one 8-byte store per value and block: pairing two rows into a 16-byte store measured slower, and so did a
+      // staging area with one bulk copy per class and block)
+      auto push_residual = [&](int k, int i, double res) {
+        const uint32_t dst = smem_u32(Rs) + (uint32_t)(k * n_e + i) * 8u, bar1 = smem_u32(&xbar[1]);
+#pragma unroll
+        for (int qq = 0; qq < kClMax; ++qq)
+          if (qq < (int)G) st_async_f64(map_to_cta(dst, (uint32_t)qq), res, map_to_cta(bar1, (uint32_t)qq));
+      };
       if (by_class) {
         if (w * RPW < nrows) {   // warp-uniform: all 32 lanes take part in the shuffles
           // find_normlv (utils.cpp:10-26) with the same operations in the same order as the thread-per-row form:
@@ -687,15 +736,8 @@ __global__ void __launch_bounds__(kFT, 1) k_traj(Geom g, Bufs b, FusedGeom fg, i
                 b.lv[(int64_t)k * n_s + i] = lc;                // the proposal's lv and residual: only the final ones are state
                 if (CL) b.R[(int64_t)k * n_s + i] = res;
               }
-              if (CL) {
-                // push the new residual into every block's copy
-                const uint32_t dst = smem_u32(Rs) + (uint32_t)(k * n_e + i) * 8u;
-#pragma unroll
-                for (int qq = 0; qq < kClMax; ++qq)
-                  if (qq < (int)G) st_dsmem(map_to_cta(dst, (uint32_t)qq), res);
-              } else {
-                __stcg(&b.R[(int64_t)k * n_s + i], res);
-              }
+              if (CL) push_residual(k, i, res);
+              else __stcg(&b.R[(int64_t)k * n_s + i], res);
             }
           }
         }
@@ -722,11 +764,7 @@ __global__ void __launch_bounds__(kFT, 1) k_traj(Geom g, Bufs b, FusedGeom fg, i
             if (CL) b.R[(int64_t)k * n_s + i] = res;
           }
           if (CL) {
-            // push the new residual into every block's copy
-            const uint32_t dst = smem_u32(Rs) + (uint32_t)(k * n_e + i) * 8u;
-#pragma unroll
-            for (int qq = 0; qq < kClMax; ++qq)
-              if (qq < (int)G) st_dsmem(map_to_cta(dst, (uint32_t)qq), res);
+            push_residual(k, i, res);
           } else {
             __stcg(&b.R[(int64_t)k * n_s + i], res);
           }
@@ -746,9 +784,12 @@ __global__ void __launch_bounds__(kFT, 1) k_traj(Geom g, Bufs b, FusedGeom fg, i
       }
     }
     if (timer) { const long long t = clk(); atomicAdd(&ctl->ph_cycles[2], (unsigned long long)(t - tk0)); tk0 = t; }
-    sync_all();
+    if (!CL) sync_all();
     if (timer) { const long long t = clk(); atomicAdd(&ctl->ph_cycles[3], (unsigned long long)(t - tk0)); }
   }
+  // cluster mode: the one barrier after the trajectory - the log-likelihood partials below are in global memory, and
+  // no block may leave while another can still store into its shared memory
+  if (CL) cluster_barrier();
   // final coefficients and momenta back to the compact global arrays (every group has finished its tiles)
   named_bar(kBarCompute, kCT);
   for (int e = ct; e < ncols; e += kCT) {
@@ -852,7 +893,8 @@ bool fused_plan(const Geom& g, int smem_optin_bytes, int cl, FusedGeom* out) {
   if (npairs > kCT * kNlpMax) return false;
   const int G = cl > 0 ? cl : g.sm_count;
   if (cl > kClMax) return false;
-  const int rpc = (n + G - 1) / G;
+  int rpc = (n + G - 1) / G;
+  if (cl > 0) rpc = (rpc + 1) & ~1;   // cluster mode: a row pair has one owner (16-byte pushes of the lv partials)
   if (rpc > kCT) return false;
   if (G > 32 * kPartSlots) return false;   // row phase: one lane sums at most kPartSlots block partials
   // smallest group whose threads keep their row pairs (x, residual, lv partial) in registers
@@ -877,7 +919,7 @@ bool fused_plan(const Geom& g, int smem_optin_bytes, int cl, FusedGeom* out) {
                                 (cl > 0 ? 0 : kCW * rpc * K)) * sizeof(double) +
                        (size_t)(ng - 1) * K * n_e * sizeof(double) +
                        (size_t)ncmax * ((3 * K + 2) * sizeof(double) + sizeof(int)) +
-                       (cl > 0 ? (size_t)2 * K * n_e * sizeof(double) : 0) + 2 * kNsMax * sizeof(uint64_t) + 256;
+                       (cl > 0 ? (size_t)(cl * K * rpc + K * n_e) * sizeof(double) : 0) + 2 * kNsMax * sizeof(uint64_t) + 256;
   const size_t tile_bytes = (size_t)TC * col_bytes;
   if ((size_t)smem_optin_bytes < other + 1024 + 2 * ng * tile_bytes) return false;
   const size_t budget = (size_t)smem_optin_bytes - other - 1024;
