@@ -359,10 +359,11 @@ int enqueue_step(htlr_handle* h, int L, bool until_energy_only = false) {
     h->fg.timing = h->fgc.timing = h->profiling ? 1 : 0;
     if (h->use_small) {
       // a restricted set that fits in one SM's shared memory: no inter-block exchange at all
-      // measured (tools/small_sweep.py, after the cluster kernel's row phase was shortened): it beats the cluster
-      // kernel up to u ~ 96 at n = 62 and u ~ 10 at n = 200 - one SM's FP64 rate bounds the softmax of the rows
+      // measured (tools/small_sweep.py, after the cluster kernel's exchange lost its barriers): it beats the cluster
+      // kernel only up to u ~ 12 at n = 62 (108 vs 117 us per iteration at u = 8) and is level with it at u = 8, n = 200 -
+      // one SM's FP64 rate bounds the softmax of the rows
       CU(launch_traj_small(g, b, L, h->smem_optin,
-                           h->cfg.algo == HTLR_ALGO_SMALL_FIRST ? (1 << 20) : std::max(4, 370000 / (g.n * g.n)), st));
+                           h->cfg.algo == HTLR_ALGO_SMALL_FIRST ? (1 << 20) : std::max(4, 46000 / (g.n * g.n)), st));
       ++nk;
     }
     if (h->use_cluster) {
@@ -660,7 +661,10 @@ void do_create(const htlr_cfg* cfg, const double* X, int64_t ldx, const double* 
         // hardware barriers) has lower latency per leapfrog step but a fraction of the bandwidth: measured
         // crossover at about 1.5 MB of X[:, iup] (tools/mode_sweep.py).
         const int cap = h->fgc.cl * h->fgc.ncmax;
-        const int by_bytes = (int)std::min<double>(1.5e6 / (8.0 * n), 2.0e9);
+        // (re-measured after the cluster-mode exchange lost its barriers: crossover at 1.5 MB for n = 500 / K = 3,
+        // 2.0 MB for n = 200 / K = 1, 2.6 - 2.8 MB for n = 1000 and 2000 / K = 2)
+        const double cross = K >= 3 ? 1.5e6 : (n >= 1000 ? 2.5e6 : 1.9e6);
+        const int by_bytes = (int)std::min<double>(cross / (8.0 * n), 2.0e9);
         const bool forced = c.algo == HTLR_ALGO_FUSED_CLUSTER || c.algo == HTLR_ALGO_CLUSTER_ONLY;
         h->fgc.cl_umax = forced ? cap : std::min(cap, by_bytes);
         h->fgc.cl_only = c.algo == HTLR_ALGO_CLUSTER_ONLY ? 1 : 0;

@@ -133,7 +133,7 @@ def test_concurrent_chains_on_one_gpu_match_their_solo_runs():
 def test_auto_uses_the_single_block_kernel_when_the_restricted_set_fits():
     """AUTO: a restricted set that fits in one SM's shared memory is run by k_traj_small; a large one is not."""
     import htlr_b200
-    small = problem(100, 30, 3, seed=4, iters_rmc=6, iters_h=2, leap_L=8, hmc_sgmcut=0.0)      # 31 columns x 100 rows (limit: 37)
+    small = problem(100, 3, 3, seed=4, iters_rmc=6, iters_h=2, leap_L=8, hmc_sgmcut=0.0)       # 4 columns x 100 rows (limit: 4)
     big = problem(100, 400, 3, seed=4, iters_rmc=6, iters_h=2, leap_L=8, hmc_sgmcut=0.0)       # 401 columns
     for args, expect in ((small, 8), (big, 0)):
         s = htlr_b200.Sampler(**args, seed=2, algo=0)
