@@ -213,6 +213,8 @@ struct htlr_handle {
   FusedGeom fgc{};
   bool use_cluster = false; // launch the cluster-mode flavour ahead of the grid-mode one
   bool use_small = false;   // launch the single-block kernel ahead of both
+  int rows_cl = 0;          // > 0: launch the row-partitioned cluster kernel (this cluster size) ahead of all of them
+  int rows_uk_max = 0;      //      largest u * K it takes
   bool skip_grid = false;   // the cluster-mode kernel covers every possible restricted set: no grid-mode launch
   int smem_optin = 0;
   unsigned long long small_base = 0;
@@ -357,6 +359,11 @@ int enqueue_step(htlr_handle* h, int L, bool until_energy_only = false) {
   if (h->fused) {
     ProfScope ps(h, 0);
     h->fg.timing = h->fgc.timing = h->profiling ? 1 : 0;
+    if (h->rows_cl > 0) {
+      // few restricted columns (u K small): every block owns a slab of rows and only the gradient is exchanged
+      CU(launch_traj_rows(g, b, L, h->rows_cl, h->rows_uk_max, st));
+      ++nk;
+    }
     if (h->use_small) {
       // a restricted set that fits in one SM's shared memory: no inter-block exchange at all
       // measured (tools/small_sweep.py, after the cluster kernel's exchange lost its barriers): it beats the cluster
@@ -443,7 +450,7 @@ int kernels_per_step(const htlr_handle* h, int L) {
   int per_grad = h->sharded ? 3 : 2;
   int n = 2 + 2 + per_grad + L * (2 + per_grad) + 1 + 1 + 1 + 1;
   if (h->fused) n = 2 + 1 + 1 + 1 + 1 + (h->skip_grid ? 0 : 1) + (h->use_cluster ? 1 : 0) +
-                     (h->use_small ? 1 : 0);
+                     (h->use_small ? 1 : 0) + (h->rows_cl > 0 ? 1 : 0);
   if (h->cfg.ptype == HTLR_PRIOR_T && h->cfg.eta > 1e-10) n += 1;
   if (h->cfg.ptype == HTLR_PRIOR_T && !(h->cfg.eta > 1e-10)) n -= 2;
   return n;
@@ -682,6 +689,18 @@ void do_create(const htlr_cfg* cfg, const double* X, int64_t ldx, const double* 
     h->use_small = h->fused && small_applies(g) &&
                    (((c.algo == HTLR_ALGO_AUTO || c.algo == HTLR_ALGO_CLUSTER_ONLY) && g.n <= 256) ||
                     c.algo == HTLR_ALGO_SMALL_FIRST);
+    if (h->fused && (((c.algo == HTLR_ALGO_AUTO || c.algo == HTLR_ALGO_CLUSTER_ONLY) && g.n >= 1000) ||
+                     c.algo == HTLR_ALGO_ROWS_FIRST)) {
+      h->rows_cl = rows_cluster_size(g);
+      // measured (tools/rows_sweep.py, us per iteration, rows kernel vs k_traj's cluster mode): n = 1000 / K = 2: 171 vs 188
+      // at u = 4, 188 vs 193 at u = 8, 221 vs 201 at u = 16; n = 1000 / K = 4: 255 vs 330 at u = 4, 343 vs 370 at u = 16,
+      // 401 vs 361 at u = 32; n = 2000 / K = 2: 185 vs 250 at u = 4, 271 vs 277 at u = 32. Below n = 1000 the softmax of a
+      // block's rows is short either way and k_traj's cluster mode is the faster one (config B default: 3.1 vs 3.7 us
+      // per leapfrog step).
+      h->rows_uk_max = c.algo == HTLR_ALGO_ROWS_FIRST ? (1 << 20) : ((K >= 3 || g.n >= 2000) ? 64 : 16);
+      if (const char* e = std::getenv("HTLR_ROWS_UK_MAX")) h->rows_uk_max = std::atoi(e);   // sweeps only
+      if (h->rows_uk_max <= 0) h->rows_cl = 0;
+    }
   }
   b.lvpart = h->dalloc<double>((size_t)std::max(g.lv_cs, g.sm_count) * K * g.n_s);
   b.red = h->dalloc<Red4>((size_t)std::max(std::max(g.e_grid, (n + 255) / 256), g.sm_count));

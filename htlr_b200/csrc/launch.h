@@ -148,6 +148,10 @@ void launch_std(int n, int p, const double* A, int64_t lda, double* out, int64_t
 bool small_applies(const Geom& g);
 cudaError_t launch_traj_small(const Geom& g, const Bufs& b, int L, int smem_bytes, int u_max, cudaStream_t st);
 
+// rows_kernel.cu: row-partitioned cluster kernel for restricted sets with few columns (only the gradient is exchanged)
+int rows_cluster_size(const Geom& g);  // cluster size it can run with on the current device, or 0
+cudaError_t launch_traj_rows(const Geom& g, const Bufs& b, int L, int cl, int uk_max, cudaStream_t st);
+
 // sigma_kernels.cu (compiled with --fmad=false)
 void launch_sigma(const Geom& g, const Bufs& b, cudaStream_t st);      // t prior: gamma draws
 void launch_tail_t(const Geom& g, const Bufs& b, cudaStream_t st);     // t prior, eta = 0: commit + sigma + record in one

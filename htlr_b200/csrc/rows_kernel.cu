@@ -1,0 +1,413 @@
+// Row-partitioned cluster kernel for restricted sets with FEW columns (u K of the order of 100 or less): the regime of
+// config B with the product defaults (n = 500, u ~ 11) and of strongly sparse fits on larger n, where k_traj's cluster
+// mode still exchanges n K partial predictors and n K residuals per block and leapfrog step.
+//
+// Here a block of the cluster owns a slab of ROWS of every restricted column (X[rows, iup] resident in its shared memory
+// for the whole trajectory), so the linear predictor, the softmax and the residual of its rows never leave the block.
+// What is exchanged per leapfrog step is the gradient: every block forms the partial sums X[rows, j]' r[rows, :] of
+// all u columns over its rows and sends the u K numbers to every block (counted asynchronous stores: st.async +
+// mbarrier complete_tx on the receiver, no fence, no cluster barrier); every block then adds the partials in block order
+// and applies the leapfrog update to its own copy of the coefficients — all copies stay bit-identical because all blocks
+// add the same numbers in the same order. One exchange of 8 u K bytes per block pair and step instead of two of 8 n K / 16.
+//
+// Same arithmetic as k_traj and k_traj_small (Fit::Traject, gibbs.cpp:390-419): all L+1 gradient evaluations in one
+// launch, the predictor carried from step to step. Launched ahead of the other trajectory kernels; it decides on the
+// device whether the restricted set is small enough (then sets Ctl::traj_done) or leaves the proposal to them.
+#include <algorithm>
+
+#include "common.cuh"
+#include "launch.h"
+
+namespace htlr {
+
+namespace {
+
+constexpr int kRT = 512;      // threads per block
+constexpr int kRCI = 4;       // columns a warp reduces at a time in the gradient phase
+constexpr int kRowsClMax = 16;
+
+__device__ __forceinline__ uint32_t r_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t r_mapa(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void r_st_async(uint32_t addr, double v, uint32_t mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f64 [%0], %1, [%2];"
+               ::"r"(addr), "d"(v), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void r_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(r_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void r_mbar_expect(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(r_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void r_mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok)
+                 : "r"(r_u32(bar)), "r"(parity)
+                 : "memory");
+  }
+}
+__device__ __forceinline__ void r_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+}  // namespace
+
+// smem_doubles: dynamic shared memory available per block, in doubles; uk_max: largest u * K the kernel takes
+template <int KT>
+__global__ void __launch_bounds__(kRT, 1) k_traj_rows(Geom g, Bufs b, int L, int smem_doubles, int uk_max) {
+  Ctl* ctl = b.ctl;
+  if (ctl->traj_done) return;
+  const int u = ctl->u;
+  const int n = g.n, n_s = g.n_s, n_e = (n + 1) & ~1;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  constexpr int NW = kRT / 32;
+  const int G = (int)gridDim.x, cta = (int)blockIdx.x;
+  const int UK = u * KT;
+  // rows of this block: an even number per block, so slabs start on 16-byte boundaries and a row pair has one owner
+  const int rpc = (((n + G - 1) / G) + 1) & ~1;
+  const int row0 = cta * rpc;
+  const int nr = max(0, min(n, row0 + rpc) - row0);        // rows of the slab
+  const int nre = max(0, min(n_e, row0 + rpc) - row0);     // ... with the pad row of an odd n (X and the residual hold 0 there)
+  const int gsrc = (n + rpc - 1) / rpc;                    // blocks that own rows (the others only keep the barriers company)
+  const int npl = nre >> 1;                                // row pairs of the slab
+  // lv phase: CH threads share a row when the slab has fewer rows than the block has threads
+  const int n32 = (rpc + 31) & ~31;
+  const int CH = n32 <= kRT / 2 ? kRT / n32 : 1;
+  if (UK > uk_max || rpc > kRT) return;
+  const size_t need = (size_t)u * rpc + (size_t)KT * rpc + (CH > 1 ? (size_t)KT * CH * n32 : 0) + (size_t)u * (4 * KT + 2) +
+                      (size_t)((UK + 1) & ~1) + 2 * (size_t)G * ((UK + 1) & ~1) + 2 * NW + 8 + (size_t)(u + 1) / 2;
+  if (need > (size_t)smem_doubles) return;       // does not fit: the other kernels take the proposal
+  extern __shared__ __align__(128) unsigned char sm_raw[];
+  const int UKe = (UK + 1) & ~1;
+  double* Xs = reinterpret_cast<double*>(sm_raw);            // [u][rpc]   this block's rows of every restricted column
+  double* Rs = Xs + (size_t)u * rpc;                          // [KT][rpc]  residual of the rows
+  double* part = Rs + (size_t)KT * rpc;                       // [KT][CH][n32] (CH > 1)
+  double* st = part + (CH > 1 ? (size_t)KT * CH * n32 : 0);   // [u][4*KT+2]: d, m, prior gradient, sig, step, increment of d
+  double* gown = st + (size_t)u * (4 * KT + 2);               // [UKe] gradient partial of this block's rows
+  double* recv = gown + UKe;                                  // [2][G][UKe] partials received (by step parity)
+  double* red = recv + 2 * (size_t)G * UKe;                   // [2*NW]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(red + 2 * NW);  // [0] TMA, [1], [2] exchange barriers by step parity
+  int* cidx = reinterpret_cast<int*>(bar + 4);                // [u]
+  constexpr int CS = 4 * KT + 2;
+  const double Cd = (double)ctl->C;
+  const uint32_t xbytes = (uint32_t)(gsrc * UK) * 8u;
+
+  if (tid == 0) {
+    r_mbar_init(&bar[0], 1);
+    r_mbar_init(&bar[1], 1);
+    r_mbar_init(&bar[2], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (nr > 0) {   // the first two steps' partials are expected from the start
+      r_mbar_expect(&bar[1], xbytes);
+      r_mbar_expect(&bar[2], xbytes);
+    }
+    if (cta == 0) ctl->cols_swept += (unsigned long long)u;   // X[:, iup] is read from memory once per trajectory here
+  }
+  for (int e = tid; e < u; e += kRT) cidx[e] = b.iup[e];
+  __syncthreads();
+  // X[rows, iup] -> shared memory, one bulk copy per column
+  const uint32_t col_bytes = (uint32_t)nre * 8u;
+  if (nre > 0) {
+    if (tid == 0) r_mbar_expect(&bar[0], col_bytes * (uint32_t)u);
+    for (int e = tid; e < u; e += kRT)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       r_u32(Xs + (size_t)e * rpc)),
+                   "l"(b.X + (int64_t)cidx[e] * g.ld + row0), "r"(col_bytes), "r"(r_u32(&bar[0]))
+                   : "memory");
+  }
+  // per-column state (every block keeps all of it) and the first prior-gradient term (gibbs.cpp:267-272, 281)
+  for (int e = tid; e < u; e += kRT) {
+    double* s = st + (size_t)e * CS;
+#pragma unroll
+    for (int k = 0; k < KT; ++k) { s[k] = b.dc[(int64_t)e * KT + k]; s[KT + k] = b.momt[(int64_t)e * KT + k]; }
+    const double sig = b.sigc[e];
+    s[3 * KT] = sig;
+    s[3 * KT + 1] = b.stepc[e];
+    double sd = s[0];
+#pragma unroll
+    for (int k = 1; k < KT; ++k) sd += s[k];
+    const double sdc = sd / Cd;
+#pragma unroll
+    for (int k = 0; k < KT; ++k) s[2 * KT + k] = (s[k] - sdc) / sig;
+  }
+  for (int e = tid; e < KT * rpc; e += kRT) {
+    const int k = e / rpc, i = e - k * rpc;
+    Rs[e] = i < nr ? b.R[(int64_t)k * n_s + row0 + i] : 0.0;
+  }
+  // lv phase ownership: thread -> (row of the slab, column chunk); per-row constants in registers
+  const int ch = CH > 1 ? tid / n32 : 0;
+  const int rloc = CH > 1 ? tid - ch * n32 : tid;   // row of the slab
+  const bool owner = ch == 0;                        // applies the softmax
+  const bool have_row = rloc < nr && (CH == 1 || tid < CH * n32);
+  double fixv[KT], yv[KT];                           // fixv: the row's running linear predictor
+  int ybv = -1;
+#pragma unroll
+  for (int k = 0; k < KT; ++k) { fixv[k] = 0; yv[k] = 0; }
+  if (owner && have_row) {
+    ybv = b.ybase[row0 + rloc];
+#pragma unroll
+    for (int k = 0; k < KT; ++k) { fixv[k] = b.lv[(int64_t)k * n_s + row0 + rloc]; yv[k] = b.ymat[(int64_t)k * n_s + row0 + rloc]; }
+  }
+  const int cpc = (u + CH - 1) / CH;
+  const int cl0 = min(u, ch * cpc), cl1 = min(u, cl0 + cpc);
+  if (nre > 0) r_mbar_wait(&bar[0], 0);
+  __syncthreads();
+  // every block's barriers exist (and are armed) before anybody stores into them
+  r_cluster_sync();
+
+  double ll_total = 0;
+  for (int s = 0; s <= L; ++s) {
+    const int par = s & 1;
+    // ================= gradient partial over this block's rows: warp <-> kRCI columns at a time =========
+    if (nr > 0) {
+      for (int c0 = w; c0 < u; c0 += NW * kRCI) {
+        double acc[kRCI][KT];
+#pragma unroll
+        for (int ci = 0; ci < kRCI; ++ci)
+#pragma unroll
+          for (int k = 0; k < KT; ++k) acc[ci][k] = 0;
+        for (int m = lane; m < npl; m += 32) {
+          double2 r[KT];
+#pragma unroll
+          for (int k = 0; k < KT; ++k) r[k] = *reinterpret_cast<const double2*>(Rs + k * rpc + 2 * m);   // pad row holds 0
+#pragma unroll
+          for (int ci = 0; ci < kRCI; ++ci) {
+            if (c0 + NW * ci < u) {
+              const double2 x = *reinterpret_cast<const double2*>(Xs + (size_t)(c0 + NW * ci) * rpc + 2 * m);
+#pragma unroll
+              for (int k = 0; k < KT; ++k) acc[ci][k] = fma(x.x, r[k].x, fma(x.y, r[k].y, acc[ci][k]));
+            }
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+          for (int ci = 0; ci < kRCI; ++ci)
+#pragma unroll
+            for (int k = 0; k < KT; ++k) acc[ci][k] += __shfl_xor_sync(0xffffffffu, acc[ci][k], o);
+        if (lane == 0) {
+#pragma unroll
+          for (int ci = 0; ci < kRCI; ++ci)
+            if (c0 + NW * ci < u) {
+#pragma unroll
+              for (int k = 0; k < KT; ++k) gown[(size_t)(c0 + NW * ci) * KT + k] = acc[ci][k];
+            }
+        }
+      }
+    }
+    __syncthreads();
+    // ================= exchange: this block's u K partials into slot `cta` of every row-owning block ============
+    if (nr > 0) {
+      const uint32_t slot = r_u32(recv + ((size_t)par * G + cta) * UKe), xb = r_u32(&bar[1 + par]);
+      for (int idx = tid; idx < UK * gsrc; idx += kRT) {
+        const int item = idx / gsrc, dest = idx - item * gsrc;
+        r_st_async(r_mapa(slot + (uint32_t)item * 8u, (uint32_t)dest), gown[item], r_mapa(xb, (uint32_t)dest));
+      }
+      // the partials of step s from every row-owning block; thread 0 arms the barrier for step s + 2 (its stores can
+      // only be sent by blocks that hold this block's partials of step s + 1, i.e. after every thread here is past
+      // this wait)
+      r_mbar_wait(&bar[1 + par], (uint32_t)((s >> 1) & 1));
+      if (tid == 0 && s + 2 <= L) r_mbar_expect(&bar[1 + par], xbytes);
+    }
+    // ================= update: thread <-> column, the same in every block (DNlogpost, MoveMomt, UpdateMomtAndDeltas) ====
+    for (int c = tid; c < u; c += kRT) {
+      double* sc = st + (size_t)c * CS;
+      const double stp = sc[3 * KT + 1], hs = stp / 2, sig = sc[3 * KT];
+      double dn[KT];
+#pragma unroll
+      for (int k = 0; k < KT; ++k) {
+        const double* rp = recv + (size_t)par * G * UKe + (size_t)c * KT + k;
+        double gsum = rp[0];
+        for (int q = 1; q < gsrc; ++q) gsum += rp[(size_t)q * UKe];   // block order: the same sum everywhere
+        const double post = gsum + sc[2 * KT + k];
+        const double kick = __dmul_rn(hs, post);
+        double mm = sc[KT + k];
+        if (s >= 1) mm = __dsub_rn(mm, kick);
+        double dnew = sc[k];
+        if (s < L) {
+          mm = __dsub_rn(mm, kick);
+          dnew = __dadd_rn(dnew, __dmul_rn(stp, mm));
+        }
+        sc[KT + k] = mm;
+        dn[k] = dnew;
+      }
+      if (s < L) {
+        double sd = dn[0];
+#pragma unroll
+        for (int k = 1; k < KT; ++k) sd += dn[k];
+        const double sdc = sd / Cd;
+#pragma unroll
+        for (int k = 0; k < KT; ++k) {
+          sc[3 * KT + 2 + k] = __dsub_rn(dn[k], sc[k]);   // what the lv phase adds
+          sc[k] = dn[k];
+          sc[2 * KT + k] = (dn[k] - sdc) / sig;
+        }
+      }
+    }
+    __syncthreads();
+    if (s == L) break;
+
+    // ================= linear predictor, softmax, residual of this block's rows =================
+    const bool last = (s == L - 1);
+    double ll = 0;
+    {
+      double a[KT];
+#pragma unroll
+      for (int k = 0; k < KT; ++k) a[k] = 0;
+      if (have_row) {
+        for (int c = cl0; c < cl1; ++c) {
+          const double x = Xs[(size_t)c * rpc + rloc];
+          const double* sc = st + (size_t)c * CS + 3 * KT + 2;
+#pragma unroll
+          for (int k = 0; k < KT; ++k) a[k] = fma(x, sc[k], a[k]);
+        }
+      }
+      if (CH > 1) {
+        if (have_row) {
+#pragma unroll
+          for (int k = 0; k < KT; ++k) part[((size_t)k * CH + ch) * n32 + rloc] = a[k];
+        }
+        __syncthreads();
+        if (have_row && owner) {
+#pragma unroll
+          for (int k = 0; k < KT; ++k) {
+            double t = part[(size_t)k * CH * n32 + rloc];
+            for (int cc = 1; cc < CH; ++cc) t += part[((size_t)k * CH + cc) * n32 + rloc];
+            a[k] = t;
+          }
+        }
+      }
+      if (have_row && owner) {
+        const int i = row0 + rloc;
+        double l[KT];
+        double m = 0.0;
+#pragma unroll
+        for (int k = 0; k < KT; ++k) { l[k] = fixv[k] + a[k]; fixv[k] = l[k]; m = fmax(m, l[k]); }
+        // find_normlv (utils.cpp:10-26), the reference's operations in the reference's order (forming the probabilities
+        // as e / se instead would save a log and an exp per step, 4-8 % of an iteration, and costs four orders of
+        // magnitude of parity margin over a chain: measured, not adopted)
+        double se = exp(0.0 - m);
+#pragma unroll
+        for (int k = 0; k < KT; ++k) se += exp(l[k] - m);
+        const double lse = log(se) + m;
+        if (ybv == 0) ll += 0.0 - lse;
+#pragma unroll
+        for (int k = 0; k < KT; ++k) {
+          const double nl = l[k] - lse;
+          if (ybv == k + 1) ll += nl;
+          const double res = exp(nl) - yv[k];
+          Rs[k * rpc + rloc] = res;
+          if (last) { b.lv[(int64_t)k * n_s + i] = l[k]; b.R[(int64_t)k * n_s + i] = res; }
+        }
+      }
+    }
+    if (last) ll_total = ll;
+    __syncthreads();
+  }
+
+  // ---- log-likelihood of the proposal: block partials in global memory, added in block order by block 0 after the one
+  // cluster barrier that also keeps every block alive until nobody can store into it any more
+  {
+    double v = warp_sum(ll_total);
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0;
+      for (int i = 0; i < NW; ++i) t += red[i];
+      b.red[cta].c = t;
+    }
+  }
+  r_cluster_sync();
+  if (cta == 0) {
+    if (tid == 0) {
+      double t = 0;
+      for (int c = 0; c < gsrc; ++c) t += __ldcg(&b.red[c].c);
+      ctl->loglike_new = t;
+      ctl->traj_done = 1;
+      ctl->small_runs += 1;
+    }
+    for (int e = tid; e < u; e += kRT) {
+      const double* s = st + (size_t)e * CS;
+#pragma unroll
+      for (int k = 0; k < KT; ++k) { b.dc[(int64_t)e * KT + k] = s[k]; b.momt[(int64_t)e * KT + k] = s[KT + k]; }
+    }
+  }
+}
+
+namespace {
+
+constexpr int kRowsSmem = 96 * 1024;   // dynamic shared memory per block
+
+template <int KT>
+cudaError_t launch_rows_k(const Geom& g, const Bufs& b, int L, int cl, int uk_max, cudaStream_t st) {
+  static PerDeviceOnce configured;
+  auto kern = k_traj_rows<KT>;
+  if (configured.needed()) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowsSmem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return e;
+    configured.mark();
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(cl);
+  cfg.blockDim = dim3(kRT);
+  cfg.dynamicSmemBytes = kRowsSmem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cl;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, g, b, L, kRowsSmem / (int)sizeof(double), uk_max);
+}
+
+}  // namespace
+
+// Cluster size the row-partitioned kernel can run with on this device (16, else 8), or 0: K <= 4, a slab of at most
+// kRT rows per block.
+int rows_cluster_size(const Geom& g) {
+  if (g.K < 1 || g.K > 4) return 0;
+  for (int cl = kRowsClMax; cl >= 8; cl >>= 1) {
+    if ((g.n + cl - 1) / cl + 1 > kRT) continue;
+    auto kern = k_traj_rows<1>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowsSmem) != cudaSuccess) continue;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) continue;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cl);
+    cfg.blockDim = dim3(kRT);
+    cfg.dynamicSmemBytes = kRowsSmem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cl;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int nclusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&nclusters, (void*)kern, &cfg) == cudaSuccess && nclusters >= 1) return cl;
+    (void)cudaGetLastError();
+  }
+  (void)cudaGetLastError();
+  return 0;
+}
+
+cudaError_t launch_traj_rows(const Geom& g, const Bufs& b, int L, int cl, int uk_max, cudaStream_t st) {
+  switch (g.K) {
+    case 1: return launch_rows_k<1>(g, b, L, cl, uk_max, st);
+    case 2: return launch_rows_k<2>(g, b, L, cl, uk_max, st);
+    case 3: return launch_rows_k<3>(g, b, L, cl, uk_max, st);
+    case 4: return launch_rows_k<4>(g, b, L, cl, uk_max, st);
+  }
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace htlr

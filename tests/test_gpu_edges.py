@@ -30,7 +30,7 @@ def _chain(args, algo, T=None, tol=1e-10, **kw):
 
 
 ALGOS = [pytest.param(1, id="two-sweep"), pytest.param(2, id="fused"), pytest.param(3, id="cluster"),
-         pytest.param(0, id="auto"), pytest.param(4, id="cluster-only"), pytest.param(6, id="small-first")]
+         pytest.param(0, id="auto"), pytest.param(4, id="cluster-only"), pytest.param(6, id="small-first"), pytest.param(7, id="rows-first")]
 
 
 @pytest.mark.parametrize("algo", ALGOS)
@@ -142,6 +142,28 @@ def test_auto_uses_the_single_block_kernel_when_the_restricted_set_fits():
         assert s.profile_get()["small_kernel_trajectories"] == expect
         s.close()
     s = htlr_b200.Sampler(**small, seed=2, algo=5)     # FUSED_NO_SMALL
+    s.run(8)
+    assert s.profile_get()["small_kernel_trajectories"] == 0
+    s.close()
+
+
+def test_auto_uses_the_row_partitioned_kernel_for_a_handful_of_columns_on_many_rows():
+    """AUTO: n >= 1000 and u K <= 16 (K <= 2) / 64 goes to k_traj_rows (every block owns a slab of rows, only the gradient is
+    exchanged); the same chain as the other algorithms to rounding, identical accept decisions."""
+    import htlr_b200
+    args = problem(1000, 5, 3, seed=11, iters_rmc=6, iters_h=2, leap_L=8, hmc_sgmcut=0.0)      # 6 columns x 1000 rows, K = 2
+    outs = {}
+    for algo in (0, 5):
+        s = htlr_b200.Sampler(**args, seed=2, algo=algo)
+        s.profile_get(reset=True)
+        s.run(8)
+        assert s.profile_get()["small_kernel_trajectories"] == (8 if algo == 0 else 0)
+        outs[algo] = s.fetch()
+        s.close()
+    assert np.array_equal(outs[0]["mchmcrej"], outs[5]["mchmcrej"])
+    assert relerr(outs[0]["mcdeltas"], outs[5]["mcdeltas"]) < 1e-10
+    big = problem(1000, 60, 3, seed=11, iters_rmc=6, iters_h=2, leap_L=8, hmc_sgmcut=0.0)      # 61 columns: u K = 122
+    s = htlr_b200.Sampler(**big, seed=2, algo=0)
     s.run(8)
     assert s.profile_get()["small_kernel_trajectories"] == 0
     s.close()

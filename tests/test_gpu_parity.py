@@ -51,7 +51,7 @@ def test_initial_state_matches_oracle():
 
 
 ALGOS = [pytest.param(1, id="two-sweep"), pytest.param(2, id="fused"), pytest.param(3, id="cluster"),
-         pytest.param(0, id="auto"), pytest.param(6, id="small-first")]
+         pytest.param(0, id="auto"), pytest.param(6, id="small-first"), pytest.param(7, id="rows-first")]
 
 
 @pytest.mark.parametrize("algo", ALGOS)
