@@ -13,11 +13,13 @@ CASES = [
     dict(n=1000, p=6000, C=3, cut=0.0, iters=12, L=50),      # streaming regime: tiles cycle through the ring
     dict(n=200, p=2500, C=2, cut=0.05, iters=150, L=20),     # one-warp groups, cluster mode
     dict(n=2048, p=900, C=5, cut=0.0, iters=10, L=12),       # 16-warp groups, K = 4
+    dict(n=1500, p=12, C=4, cut=0.0, iters=60, L=30),        # a handful of columns on many rows: the row-partitioned kernel
 ]
 
 
 @pytest.mark.parametrize("algo", [pytest.param(1, id="two-sweep"), pytest.param(2, id="fused"),
-                                  pytest.param(3, id="cluster"), pytest.param(0, id="auto")])
+                                  pytest.param(3, id="cluster"), pytest.param(0, id="auto"),
+                                  pytest.param(7, id="rows-first")])
 @pytest.mark.parametrize("case", CASES, ids=lambda c: f"n{c['n']}-p{c['p']}-K{c['C'] - 1}")
 def test_same_key_gives_bit_identical_chains(case, algo):
     import htlr_b200
