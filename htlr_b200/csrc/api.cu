@@ -361,7 +361,7 @@ int enqueue_step(htlr_handle* h, int L, bool until_energy_only = false) {
     h->fg.timing = h->fgc.timing = h->profiling ? 1 : 0;
     if (h->rows_cl > 0) {
       // few restricted columns (u K small): every block owns a slab of rows and only the gradient is exchanged
-      CU(launch_traj_rows(g, b, L, h->rows_cl, h->rows_uk_max, st));
+      CU(launch_traj_rows(g, b, L, h->rows_cl, h->rows_uk_max, h->smem_optin, st));
       ++nk;
     }
     if (h->use_small) {
@@ -689,15 +689,15 @@ void do_create(const htlr_cfg* cfg, const double* X, int64_t ldx, const double* 
     h->use_small = h->fused && small_applies(g) &&
                    (((c.algo == HTLR_ALGO_AUTO || c.algo == HTLR_ALGO_CLUSTER_ONLY) && g.n <= 256) ||
                     c.algo == HTLR_ALGO_SMALL_FIRST);
-    if (h->fused && (((c.algo == HTLR_ALGO_AUTO || c.algo == HTLR_ALGO_CLUSTER_ONLY) && g.n >= 1000) ||
+    // Row-partitioned kernel: largest restricted set (columns) it is handed, from tools/rows_sweep.py (us per iteration
+    // against k_traj's cluster mode over n = 300..2000, K = 1..4, u = 4..128; e.g. n = 1000 / K = 4 / u = 8: 220 vs 338,
+    // n = 500 / K = 3 / u = 8: 188 vs 210, n = 500 / K = 1: never). Rows: K = 1..4; columns: n < 800, n < 1500, n >= 1500.
+    static const int kRowsUMax[4][3] = {{0, 0, 32}, {12, 12, 32}, {8, 16, 64}, {16, 64, 32}};
+    const int rows_u_max = (K <= 4 && n >= 300) ? kRowsUMax[K - 1][n >= 1500 ? 2 : (n >= 800 ? 1 : 0)] : 0;
+    if (h->fused && (((c.algo == HTLR_ALGO_AUTO || c.algo == HTLR_ALGO_CLUSTER_ONLY) && rows_u_max > 0) ||
                      c.algo == HTLR_ALGO_ROWS_FIRST)) {
-      h->rows_cl = rows_cluster_size(g);
-      // measured (tools/rows_sweep.py, us per iteration, rows kernel vs k_traj's cluster mode): n = 1000 / K = 2: 171 vs 188
-      // at u = 4, 188 vs 193 at u = 8, 221 vs 201 at u = 16; n = 1000 / K = 4: 255 vs 330 at u = 4, 343 vs 370 at u = 16,
-      // 401 vs 361 at u = 32; n = 2000 / K = 2: 185 vs 250 at u = 4, 271 vs 277 at u = 32. Below n = 1000 the softmax of a
-      // block's rows is short either way and k_traj's cluster mode is the faster one (config B default: 3.1 vs 3.7 us
-      // per leapfrog step).
-      h->rows_uk_max = c.algo == HTLR_ALGO_ROWS_FIRST ? (1 << 20) : ((K >= 3 || g.n >= 2000) ? 64 : 16);
+      h->rows_cl = rows_cluster_size(g, dev.smem_optin);
+      h->rows_uk_max = c.algo == HTLR_ALGO_ROWS_FIRST ? (1 << 20) : rows_u_max * K;
       if (const char* e = std::getenv("HTLR_ROWS_UK_MAX")) h->rows_uk_max = std::atoi(e);   // sweeps only
       if (h->rows_uk_max <= 0) h->rows_cl = 0;
     }

@@ -149,8 +149,8 @@ bool small_applies(const Geom& g);
 cudaError_t launch_traj_small(const Geom& g, const Bufs& b, int L, int smem_bytes, int u_max, cudaStream_t st);
 
 // rows_kernel.cu: row-partitioned cluster kernel for restricted sets with few columns (only the gradient is exchanged)
-int rows_cluster_size(const Geom& g);  // cluster size it can run with on the current device, or 0
-cudaError_t launch_traj_rows(const Geom& g, const Bufs& b, int L, int cl, int uk_max, cudaStream_t st);
+int rows_cluster_size(const Geom& g, int smem_bytes);  // cluster size it can run with on the current device, or 0
+cudaError_t launch_traj_rows(const Geom& g, const Bufs& b, int L, int cl, int uk_max, int smem_bytes, cudaStream_t st);
 
 // sigma_kernels.cu (compiled with --fmad=false)
 void launch_sigma(const Geom& g, const Bufs& b, cudaStream_t st);      // t prior: gamma draws

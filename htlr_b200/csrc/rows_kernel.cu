@@ -80,8 +80,13 @@ __global__ void __launch_bounds__(kRT, 1) k_traj_rows(Geom g, Bufs b, int L, int
   const int n32 = (rpc + 31) & ~31;
   const int CH = n32 <= kRT / 2 ? kRT / n32 : 1;
   if (UK > uk_max || rpc > kRT) return;
+  // the gradient exchange has two hops: item i = (column, class) is summed by block i % gsrc (its owner), which then
+  // sends the sum to every block - 2 u K stores sent and received per block and step instead of 16 u K (a counted store
+  // costs the receiver ~4.5 cycles: all-to-all was 1.3 us per step at u K = 36)
+  const int IPO = (UK + gsrc - 1) / gsrc, IPOe = (IPO + 1) & ~1;      // items per owner
+  const int mine = (cta < gsrc && UK > cta) ? (UK - 1 - cta) / gsrc + 1 : 0;   // items this block owns
   const size_t need = (size_t)u * rpc + (size_t)KT * rpc + (CH > 1 ? (size_t)KT * CH * n32 : 0) + (size_t)u * (4 * KT + 2) +
-                      (size_t)((UK + 1) & ~1) + 2 * (size_t)G * ((UK + 1) & ~1) + 2 * NW + 8 + (size_t)(u + 1) / 2;
+                      3 * (size_t)((UK + 1) & ~1) + 2 * (size_t)G * IPOe + 2 * NW + 10 + (size_t)(u + 1) / 2;
   if (need > (size_t)smem_doubles) return;       // does not fit: the other kernels take the proposal
   extern __shared__ __align__(128) unsigned char sm_raw[];
   const int UKe = (UK + 1) & ~1;
@@ -90,22 +95,26 @@ __global__ void __launch_bounds__(kRT, 1) k_traj_rows(Geom g, Bufs b, int L, int
   double* part = Rs + (size_t)KT * rpc;                       // [KT][CH][n32] (CH > 1)
   double* st = part + (CH > 1 ? (size_t)KT * CH * n32 : 0);   // [u][4*KT+2]: d, m, prior gradient, sig, step, increment of d
   double* gown = st + (size_t)u * (4 * KT + 2);               // [UKe] gradient partial of this block's rows
-  double* recv = gown + UKe;                                  // [2][G][UKe] partials received (by step parity)
-  double* red = recv + 2 * (size_t)G * UKe;                   // [2*NW]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(red + 2 * NW);  // [0] TMA, [1], [2] exchange barriers by step parity
-  int* cidx = reinterpret_cast<int*>(bar + 4);                // [u]
+  double* recv = gown + UKe;                                  // [2][G][IPOe] partials of the items this block owns (by step parity)
+  double* gfull = recv + 2 * (size_t)G * IPOe;                // [2][UKe] summed gradient, as sent by the owners (by step parity)
+  double* red = gfull + 2 * (size_t)UKe;                      // [2*NW]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(red + 2 * NW);  // [0] TMA, [1], [2] partials arrived, [3], [4] sums arrived (by step parity)
+  int* cidx = reinterpret_cast<int*>(bar + 6);                // [u]
   constexpr int CS = 4 * KT + 2;
   const double Cd = (double)ctl->C;
-  const uint32_t xbytes = (uint32_t)(gsrc * UK) * 8u;
+  const uint32_t abytes = (uint32_t)(gsrc * mine) * 8u, bbytes = (uint32_t)UK * 8u;
 
   if (tid == 0) {
     r_mbar_init(&bar[0], 1);
     r_mbar_init(&bar[1], 1);
     r_mbar_init(&bar[2], 1);
+    r_mbar_init(&bar[3], 1);
+    r_mbar_init(&bar[4], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    if (nr > 0) {   // the first two steps' partials are expected from the start
-      r_mbar_expect(&bar[1], xbytes);
-      r_mbar_expect(&bar[2], xbytes);
+    if (nr > 0) {   // the first two steps' partials and sums are expected from the start
+      if (mine > 0) { r_mbar_expect(&bar[1], abytes); r_mbar_expect(&bar[2], abytes); }
+      r_mbar_expect(&bar[3], bbytes);
+      r_mbar_expect(&bar[4], bbytes);
     }
     if (cta == 0) ctl->cols_swept += (unsigned long long)u;   // X[:, iup] is read from memory once per trajectory here
   }
@@ -156,6 +165,21 @@ __global__ void __launch_bounds__(kRT, 1) k_traj_rows(Geom g, Bufs b, int L, int
   }
   const int cpc = (u + CH - 1) / CH;
   const int cl0 = min(u, ch * cpc), cl1 = min(u, cl0 + cpc);
+  // Alternative mapping of the lv phase, used when the slab fits it: one LANE per (row, class), class 0 (lv = 0) included.
+  // The row's C exponentials, and then its K residual exponentials, run side by side instead of one after the other in
+  // one thread (2K+1 exps and a log in sequence): the chain per row is exp, log, exp whatever K is (like k_traj's row phase).
+  constexpr int LPR = KT + 1;
+  constexpr int RPW = 32 / LPR;
+  const bool by_class = KT >= 2 && rpc <= NW * RPW;
+  const int cr = lane / LPR, cc = lane - cr * LPR;       // this lane's row within the warp, and class
+  const int crow = w * RPW + cr;                          // row of the slab
+  const bool chave = by_class && lane < RPW * LPR && crow < nr;
+  double cfix = 0.0, cy = 0.0;                            // by_class: running predictor and one-hot entry of (row, class)
+  int cyb = -1;
+  if (chave) {
+    cyb = b.ybase[row0 + crow];
+    if (cc >= 1) { cfix = b.lv[(int64_t)(cc - 1) * n_s + row0 + crow]; cy = b.ymat[(int64_t)(cc - 1) * n_s + row0 + crow]; }
+  }
   if (nre > 0) r_mbar_wait(&bar[0], 0);
   __syncthreads();
   // every block's barriers exist (and are armed) before anybody stores into them
@@ -202,18 +226,37 @@ __global__ void __launch_bounds__(kRT, 1) k_traj_rows(Geom g, Bufs b, int L, int
       }
     }
     __syncthreads();
-    // ================= exchange: this block's u K partials into slot `cta` of every row-owning block ============
+    // ================= exchange, hop 1: this block's partial of item i to the item's owner (block i % gsrc) ============
     if (nr > 0) {
-      const uint32_t slot = r_u32(recv + ((size_t)par * G + cta) * UKe), xb = r_u32(&bar[1 + par]);
-      for (int idx = tid; idx < UK * gsrc; idx += kRT) {
-        const int item = idx / gsrc, dest = idx - item * gsrc;
-        r_st_async(r_mapa(slot + (uint32_t)item * 8u, (uint32_t)dest), gown[item], r_mapa(xb, (uint32_t)dest));
+      const uint32_t ph = (uint32_t)((s >> 1) & 1);
+      {
+        const uint32_t base = r_u32(recv + ((size_t)par * G + cta) * IPOe), xa = r_u32(&bar[1 + par]);
+        for (int item = tid; item < UK; item += kRT) {
+          const int slot = item / gsrc, own = item - slot * gsrc;
+          r_st_async(r_mapa(base + (uint32_t)slot * 8u, (uint32_t)own), gown[item], r_mapa(xa, (uint32_t)own));
+        }
       }
-      // the partials of step s from every row-owning block; thread 0 arms the barrier for step s + 2 (its stores can
-      // only be sent by blocks that hold this block's partials of step s + 1, i.e. after every thread here is past
-      // this wait)
-      r_mbar_wait(&bar[1 + par], (uint32_t)((s >> 1) & 1));
-      if (tid == 0 && s + 2 <= L) r_mbar_expect(&bar[1 + par], xbytes);
+      // ---- hop 2: the owner adds the partials of its items in block order and sends the sums to every block. A barrier
+      // is armed for step s + 2 by thread 0 right after its wait for step s: stores of step s + 2 can only come from blocks
+      // that are past step s + 1, which needs this block's contribution to step s + 1, sent after every wait of step s.
+      if (mine > 0) {
+        r_mbar_wait(&bar[1 + par], ph);
+        if (tid == 0 && s + 2 <= L) r_mbar_expect(&bar[1 + par], abytes);
+        const uint32_t gb = r_u32(gfull + (size_t)par * UKe), xb = r_u32(&bar[3 + par]);
+        for (int idx = tid; idx < mine * gsrc; idx += kRT) {
+          const int slot = idx / gsrc, dest = idx - slot * gsrc;
+          const double* rp = recv + (size_t)par * G * IPOe + slot;
+          double pv[kRowsClMax];   // every load is issued before the first add
+#pragma unroll
+          for (int q = 0; q < kRowsClMax; ++q) pv[q] = q < gsrc ? rp[(size_t)q * IPOe] : 0.0;
+          double gsum = pv[0];
+#pragma unroll
+          for (int q = 1; q < kRowsClMax; ++q) gsum += pv[q];
+          r_st_async(r_mapa(gb + (uint32_t)(slot * gsrc + cta) * 8u, (uint32_t)dest), gsum, r_mapa(xb, (uint32_t)dest));
+        }
+      }
+      r_mbar_wait(&bar[3 + par], ph);
+      if (tid == 0 && s + 2 <= L) r_mbar_expect(&bar[3 + par], bbytes);
     }
     // ================= update: thread <-> column, the same in every block (DNlogpost, MoveMomt, UpdateMomtAndDeltas) ====
     for (int c = tid; c < u; c += kRT) {
@@ -222,10 +265,7 @@ __global__ void __launch_bounds__(kRT, 1) k_traj_rows(Geom g, Bufs b, int L, int
       double dn[KT];
 #pragma unroll
       for (int k = 0; k < KT; ++k) {
-        const double* rp = recv + (size_t)par * G * UKe + (size_t)c * KT + k;
-        double gsum = rp[0];
-        for (int q = 1; q < gsrc; ++q) gsum += rp[(size_t)q * UKe];   // block order: the same sum everywhere
-        const double post = gsum + sc[2 * KT + k];
+        const double post = gfull[(size_t)par * UKe + (size_t)c * KT + k] + sc[2 * KT + k];   // the same number in every block
         const double kick = __dmul_rn(hs, post);
         double mm = sc[KT + k];
         if (s >= 1) mm = __dsub_rn(mm, kick);
@@ -256,7 +296,49 @@ __global__ void __launch_bounds__(kRT, 1) k_traj_rows(Geom g, Bufs b, int L, int
     // ================= linear predictor, softmax, residual of this block's rows =================
     const bool last = (s == L - 1);
     double ll = 0;
-    {
+    if (by_class) {
+      if (w * RPW < nr) {   // warp-uniform: all 32 lanes take part in the shuffles
+        // increment of the predictor of (row, class): four strided chains over the columns, added in a fixed order
+        double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        if (chave && cc >= 1) {
+          const double* xr = Xs + crow;
+          const double* sc = st + 3 * KT + 2 + (cc - 1);
+          int c = 0;
+          for (; c + 3 < u; c += 4) {
+            a0 = fma(xr[(size_t)c * rpc], sc[(size_t)c * CS], a0);
+            a1 = fma(xr[(size_t)(c + 1) * rpc], sc[(size_t)(c + 1) * CS], a1);
+            a2 = fma(xr[(size_t)(c + 2) * rpc], sc[(size_t)(c + 2) * CS], a2);
+            a3 = fma(xr[(size_t)(c + 3) * rpc], sc[(size_t)(c + 3) * CS], a3);
+          }
+          for (; c < u; ++c) a0 = fma(xr[(size_t)c * rpc], sc[(size_t)c * CS], a0);
+        }
+        const double lc = cc >= 1 ? cfix + ((a0 + a1) + (a2 + a3)) : 0.0;
+        cfix = lc;
+        // find_normlv (utils.cpp:10-26): m = max(0, l_1..l_K); se = exp(0 - m) + exp(l_1 - m) + ... (left to right);
+        // lse = log(se) + m - the reference's operations in the reference's order
+        const int rb = min(cr, RPW - 1) * LPR;   // first lane of this lane's row
+        double m = 0.0;
+#pragma unroll
+        for (int q = 0; q < LPR; ++q) m = fmax(m, __shfl_sync(0xffffffffu, lc, rb + q));
+        const double e = exp(lc - m);
+        double se = __shfl_sync(0xffffffffu, e, rb);
+#pragma unroll
+        for (int q = 1; q < LPR; ++q) se += __shfl_sync(0xffffffffu, e, rb + q);
+        const double lse = log(se) + m;
+        const double nl = lc - lse;
+        if (chave) {
+          if (cyb == cc) ll = nl;
+          if (cc >= 1) {
+            const double res = exp(nl) - cy;
+            Rs[(cc - 1) * rpc + crow] = res;
+            if (last) {
+              b.lv[(int64_t)(cc - 1) * n_s + row0 + crow] = lc;
+              b.R[(int64_t)(cc - 1) * n_s + row0 + crow] = res;
+            }
+          }
+        }
+      }
+    } else {
       double a[KT];
 #pragma unroll
       for (int k = 0; k < KT; ++k) a[k] = 0;
@@ -342,10 +424,11 @@ __global__ void __launch_bounds__(kRT, 1) k_traj_rows(Geom g, Bufs b, int L, int
 
 namespace {
 
-constexpr int kRowsSmem = 96 * 1024;   // dynamic shared memory per block
+// Dynamic shared memory per block: the device maximum, like k_traj - a launch with another shared-memory carve-out
+// between two k_traj launches costs ~10 us of reconfiguration per iteration even when the kernel returns at once.
 
 template <int KT>
-cudaError_t launch_rows_k(const Geom& g, const Bufs& b, int L, int cl, int uk_max, cudaStream_t st) {
+cudaError_t launch_rows_k(const Geom& g, const Bufs& b, int L, int cl, int uk_max, int kRowsSmem, cudaStream_t st) {
   static PerDeviceOnce configured;
   auto kern = k_traj_rows<KT>;
   if (configured.needed()) {
@@ -374,7 +457,7 @@ cudaError_t launch_rows_k(const Geom& g, const Bufs& b, int L, int cl, int uk_ma
 
 // Cluster size the row-partitioned kernel can run with on this device (16, else 8), or 0: K <= 4, a slab of at most
 // kRT rows per block.
-int rows_cluster_size(const Geom& g) {
+int rows_cluster_size(const Geom& g, int kRowsSmem) {
   if (g.K < 1 || g.K > 4) return 0;
   for (int cl = kRowsClMax; cl >= 8; cl >>= 1) {
     if ((g.n + cl - 1) / cl + 1 > kRT) continue;
@@ -400,12 +483,12 @@ int rows_cluster_size(const Geom& g) {
   return 0;
 }
 
-cudaError_t launch_traj_rows(const Geom& g, const Bufs& b, int L, int cl, int uk_max, cudaStream_t st) {
+cudaError_t launch_traj_rows(const Geom& g, const Bufs& b, int L, int cl, int uk_max, int smem_bytes, cudaStream_t st) {
   switch (g.K) {
-    case 1: return launch_rows_k<1>(g, b, L, cl, uk_max, st);
-    case 2: return launch_rows_k<2>(g, b, L, cl, uk_max, st);
-    case 3: return launch_rows_k<3>(g, b, L, cl, uk_max, st);
-    case 4: return launch_rows_k<4>(g, b, L, cl, uk_max, st);
+    case 1: return launch_rows_k<1>(g, b, L, cl, uk_max, smem_bytes, st);
+    case 2: return launch_rows_k<2>(g, b, L, cl, uk_max, smem_bytes, st);
+    case 3: return launch_rows_k<3>(g, b, L, cl, uk_max, smem_bytes, st);
+    case 4: return launch_rows_k<4>(g, b, L, cl, uk_max, smem_bytes, st);
   }
   return cudaErrorInvalidValue;
 }

@@ -62,8 +62,8 @@ enum { HTLR_RNG_DEVICE = 0, HTLR_RNG_INJECT = 1 };
  * entirely inside one SM (two __syncthreads per leapfrog step) whenever X[:, iup] fits in its shared memory
  * and it is the faster choice (measured: n <= 256 and u <= max(4, 46000 / n^2), e.g. the first iterations of config A);
  * FUSED_NO_SMALL is AUTO without it, SMALL_FIRST uses it whenever it fits (tests).
- * For n >= 1000 AUTO also launches, ahead of everything, a row-partitioned cluster kernel for restricted sets of a
- * handful of columns (u K <= 16, or <= 64 for K >= 3 or n >= 2000): every block owns a slab of rows, only the u K
+ * For n >= 300 and K <= 4 AUTO also launches, ahead of everything, a row-partitioned cluster kernel for restricted
+ * sets of a handful of columns (8 .. 64 depending on n and K, measured): every block owns a slab of rows, only the u K
  * gradient partials are exchanged per leapfrog step; ROWS_FIRST uses it whenever it fits (tests).
  * CLUSTER_ONLY: FUSED_CLUSTER without the all-SM fallback launch, so that several chains (handles) can run
  *            concurrently on one GPU, each on its own 16-SM cluster (config D: 4 chains / folds per GPU). A

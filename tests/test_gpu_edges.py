@@ -148,8 +148,8 @@ def test_auto_uses_the_single_block_kernel_when_the_restricted_set_fits():
 
 
 def test_auto_uses_the_row_partitioned_kernel_for_a_handful_of_columns_on_many_rows():
-    """AUTO: n >= 1000 and u K <= 16 (K <= 2) / 64 goes to k_traj_rows (every block owns a slab of rows, only the gradient is
-    exchanged); the same chain as the other algorithms to rounding, identical accept decisions."""
+    """AUTO: a handful of columns (here 6 <= 12 at n = 1000, K = 2) goes to k_traj_rows (every block owns a slab of rows, only
+    the gradient is exchanged); the same chain as the other algorithms to rounding, identical accept decisions."""
     import htlr_b200
     args = problem(1000, 5, 3, seed=11, iters_rmc=6, iters_h=2, leap_L=8, hmc_sgmcut=0.0)      # 6 columns x 1000 rows, K = 2
     outs = {}

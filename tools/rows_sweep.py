@@ -5,8 +5,8 @@ import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, htlr_b200
 from tests.helpers import problem
-for n, C in ((62, 2), (200, 2), (500, 4), (1000, 3), (1000, 5), (2000, 3)):
-    for u in (4, 8, 16, 32, 64, 128, 256):
+for n, C in [(n, C) for n in (300, 500, 1000, 2000) for C in (2, 3, 4, 5)]:
+    for u in (4, 8, 12, 16, 24, 32, 64, 128):
         K = C - 1
         if u * K > 1024:
             continue
