@@ -14,6 +14,7 @@
 // launch, the predictor carried from step to step. Launched ahead of the other trajectory kernels; it decides on the
 // device whether the restricted set is small enough (then sets Ctl::traj_done) or leaves the proposal to them.
 #include <algorithm>
+#include <type_traits>
 
 #include "common.cuh"
 #include "launch.h"
@@ -209,12 +210,23 @@ __global__ void __launch_bounds__(kRT, 1) k_traj_rows(Geom g, Bufs b, int L, int
             }
           }
         }
+        // xor-shuffle trees of the columns the warp really has, interleaved (one fully unrolled variant per count, chosen
+        // by a warp-uniform branch): an SM retires about one warp shuffle per cycle, and 16 warps reducing kRCI x K values
+        // each whatever the number of columns were the longest phase of a leapfrog step with few columns
+        auto tree = [&](auto nc_) {
+          constexpr int nc = decltype(nc_)::value;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
+          for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-          for (int ci = 0; ci < kRCI; ++ci)
+            for (int ci = 0; ci < nc; ++ci)
 #pragma unroll
-            for (int k = 0; k < KT; ++k) acc[ci][k] += __shfl_xor_sync(0xffffffffu, acc[ci][k], o);
+              for (int k = 0; k < KT; ++k) acc[ci][k] += __shfl_xor_sync(0xffffffffu, acc[ci][k], o);
+        };
+        const int nci = (u - c0 + NW - 1) / NW;   // columns c0, c0 + NW, ... below u
+        if (nci >= 4) tree(std::integral_constant<int, 4>{});
+        else if (nci == 3) tree(std::integral_constant<int, 3>{});
+        else if (nci == 2) tree(std::integral_constant<int, 2>{});
+        else tree(std::integral_constant<int, 1>{});
         if (lane == 0) {
 #pragma unroll
           for (int ci = 0; ci < kRCI; ++ci)

@@ -15,6 +15,7 @@
 // Launched ahead of the cluster-mode and grid-mode kernels; it decides on the device whether the restricted set
 // fits (then sets Ctl::traj_done so the others return at once) or leaves the proposal to them.
 #include <algorithm>
+#include <type_traits>
 
 #include "common.cuh"
 #include "launch.h"
@@ -155,12 +156,23 @@ __global__ void __launch_bounds__(kST, 1) k_traj_small(Geom g, Bufs b, int L, in
           }
         }
       }
+      // xor-shuffle trees of the columns the warp really has, interleaved (one fully unrolled variant per count, chosen
+      // by a warp-uniform branch): an SM retires about one warp shuffle per cycle, and 16 warps reducing kCI x K values
+      // each whatever the number of columns were the longest phase of a leapfrog step with few columns
+      auto tree = [&](auto nc_) {
+        constexpr int nc = decltype(nc_)::value;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1)
+        for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-        for (int ci = 0; ci < kCI; ++ci)
+          for (int ci = 0; ci < nc; ++ci)
 #pragma unroll
-          for (int k = 0; k < KT; ++k) acc[ci][k] += __shfl_xor_sync(0xffffffffu, acc[ci][k], o);
+            for (int k = 0; k < KT; ++k) acc[ci][k] += __shfl_xor_sync(0xffffffffu, acc[ci][k], o);
+      };
+      const int nci = (u - c0 + NW - 1) / NW;   // columns c0, c0 + NW, ... below u
+      if (nci >= 4) tree(std::integral_constant<int, 4>{});
+      else if (nci == 3) tree(std::integral_constant<int, 3>{});
+      else if (nci == 2) tree(std::integral_constant<int, 2>{});
+      else tree(std::integral_constant<int, 1>{});
       if (lane == 0) {
 #pragma unroll
         for (int ci = 0; ci < kCI; ++ci)
