@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(kRT, 1) k_traj_rows(Geom g, Bufs b, int L, int
   const int IPO = (UK + gsrc - 1) / gsrc, IPOe = (IPO + 1) & ~1;      // items per owner
   const int mine = (cta < gsrc && UK > cta) ? (UK - 1 - cta) / gsrc + 1 : 0;   // items this block owns
   const size_t need = (size_t)u * rpc + (size_t)KT * rpc + (CH > 1 ? (size_t)KT * CH * n32 : 0) + (size_t)u * (4 * KT + 2) +
-                      3 * (size_t)((UK + 1) & ~1) + 2 * (size_t)G * IPOe + 2 * NW + 10 + (size_t)(u + 1) / 2;
+                      2 * (size_t)((UK + 1) & ~1) + 2 * (size_t)G * IPOe + 2 * NW + 10 + (size_t)(u + 1) / 2;
   if (need > (size_t)smem_doubles) return;       // does not fit: the other kernels take the proposal
   extern __shared__ __align__(128) unsigned char sm_raw[];
   const int UKe = (UK + 1) & ~1;
@@ -95,8 +95,7 @@ __global__ void __launch_bounds__(kRT, 1) k_traj_rows(Geom g, Bufs b, int L, int
   double* Rs = Xs + (size_t)u * rpc;                          // [KT][rpc]  residual of the rows
   double* part = Rs + (size_t)KT * rpc;                       // [KT][CH][n32] (CH > 1)
   double* st = part + (CH > 1 ? (size_t)KT * CH * n32 : 0);   // [u][4*KT+2]: d, m, prior gradient, sig, step, increment of d
-  double* gown = st + (size_t)u * (4 * KT + 2);               // [UKe] gradient partial of this block's rows
-  double* recv = gown + UKe;                                  // [2][G][IPOe] partials of the items this block owns (by step parity)
+  double* recv = st + (size_t)u * (4 * KT + 2);                                    // [2][G][IPOe] partials of the items this block owns (by step parity)
   double* gfull = recv + 2 * (size_t)G * IPOe;                // [2][UKe] summed gradient, as sent by the owners (by step parity)
   double* red = gfull + 2 * (size_t)UKe;                      // [2*NW]
   uint64_t* bar = reinterpret_cast<uint64_t*>(red + 2 * NW);  // [0] TMA, [1], [2] partials arrived, [3], [4] sums arrived (by step parity)
@@ -227,27 +226,28 @@ __global__ void __launch_bounds__(kRT, 1) k_traj_rows(Geom g, Bufs b, int L, int
         else if (nci == 3) tree(std::integral_constant<int, 3>{});
         else if (nci == 2) tree(std::integral_constant<int, 2>{});
         else tree(std::integral_constant<int, 1>{});
-        if (lane == 0) {
+        // ---- exchange, hop 1, straight from the registers (every lane holds the totals after the xor trees): lane
+        // ci * KT + k sends this block's partial of item (column c0 + NW ci, class k) to the item's owner, block item % gsrc
+        {
+          double v = 0.0;
 #pragma unroll
           for (int ci = 0; ci < kRCI; ++ci)
-            if (c0 + NW * ci < u) {
 #pragma unroll
-              for (int k = 0; k < KT; ++k) gown[(size_t)(c0 + NW * ci) * KT + k] = acc[ci][k];
-            }
+            for (int k = 0; k < KT; ++k)
+              if (lane == ci * KT + k) v = acc[ci][k];
+          const int ci = lane / KT;
+          if (ci < kRCI && c0 + NW * ci < u) {
+            const int item = (c0 + NW * ci) * KT + (lane - ci * KT);
+            const int slot = item / gsrc, own = item - slot * gsrc;
+            r_st_async(r_mapa(r_u32(recv + ((size_t)par * G + cta) * IPOe) + (uint32_t)slot * 8u, (uint32_t)own), v,
+                       r_mapa(r_u32(&bar[1 + par]), (uint32_t)own));
+          }
         }
       }
     }
-    __syncthreads();
-    // ================= exchange, hop 1: this block's partial of item i to the item's owner (block i % gsrc) ============
+    // ================= exchange, hop 2 ============
     if (nr > 0) {
       const uint32_t ph = (uint32_t)((s >> 1) & 1);
-      {
-        const uint32_t base = r_u32(recv + ((size_t)par * G + cta) * IPOe), xa = r_u32(&bar[1 + par]);
-        for (int item = tid; item < UK; item += kRT) {
-          const int slot = item / gsrc, own = item - slot * gsrc;
-          r_st_async(r_mapa(base + (uint32_t)slot * 8u, (uint32_t)own), gown[item], r_mapa(xa, (uint32_t)own));
-        }
-      }
       // ---- hop 2: the owner adds the partials of its items in block order and sends the sums to every block. A barrier
       // is armed for step s + 2 by thread 0 right after its wait for step s: stores of step s + 2 can only come from blocks
       // that are past step s + 1, which needs this block's contribution to step s + 1, sent after every wait of step s.
@@ -270,35 +270,43 @@ __global__ void __launch_bounds__(kRT, 1) k_traj_rows(Geom g, Bufs b, int L, int
       r_mbar_wait(&bar[3 + par], ph);
       if (tid == 0 && s + 2 <= L) r_mbar_expect(&bar[3 + par], bbytes);
     }
-    // ================= update: thread <-> column, the same in every block (DNlogpost, MoveMomt, UpdateMomtAndDeltas) ====
-    for (int c = tid; c < u; c += kRT) {
-      double* sc = st + (size_t)c * CS;
-      const double stp = sc[3 * KT + 1], hs = stp / 2, sig = sc[3 * KT];
-      double dn[KT];
-#pragma unroll
-      for (int k = 0; k < KT; ++k) {
-        const double post = gfull[(size_t)par * UKe + (size_t)c * KT + k] + sc[2 * KT + k];   // the same number in every block
-        const double kick = __dmul_rn(hs, post);
-        double mm = sc[KT + k];
-        if (s >= 1) mm = __dsub_rn(mm, kick);
-        double dnew = sc[k];
-        if (s < L) {
-          mm = __dsub_rn(mm, kick);
-          dnew = __dadd_rn(dnew, __dmul_rn(stp, mm));
+    // ================= update: lane <-> (column, class), the same in every block (DNlogpost, MoveMomt,
+    // UpdateMomtAndDeltas, next prior gradient). A column's K lanes are neighbours inside a warp; the sum of the new
+    // coefficients over the classes goes through shuffles, in class order.
+    {
+      constexpr int CPW = 32 / KT;                          // columns per warp
+      const int ucl = lane / KT, uk = lane - ucl * KT;
+      for (int cb = w * CPW; cb < u; cb += NW * CPW) {      // warp-uniform
+        const int c = cb + ucl;
+        const bool act = lane < CPW * KT && c < u;
+        double* sc = st + (size_t)(act ? c : 0) * CS;
+        double dnk = 0.0, dold = 0.0, sig = 1.0;
+        if (act) {
+          const double stp = sc[3 * KT + 1], hs = stp / 2;
+          sig = sc[3 * KT];
+          const double post = gfull[(size_t)par * UKe + (size_t)c * KT + uk] + sc[2 * KT + uk];   // the same number in every block
+          const double kick = __dmul_rn(hs, post);
+          double mm = sc[KT + uk];
+          if (s >= 1) mm = __dsub_rn(mm, kick);
+          dold = sc[uk];
+          dnk = dold;
+          if (s < L) {
+            mm = __dsub_rn(mm, kick);
+            dnk = __dadd_rn(dold, __dmul_rn(stp, mm));
+          }
+          sc[KT + uk] = mm;
         }
-        sc[KT + k] = mm;
-        dn[k] = dnew;
-      }
-      if (s < L) {
-        double sd = dn[0];
+        if (s < L) {
+          const int base = ucl * KT;
+          double sd = __shfl_sync(0xffffffffu, dnk, base);
 #pragma unroll
-        for (int k = 1; k < KT; ++k) sd += dn[k];
-        const double sdc = sd / Cd;
-#pragma unroll
-        for (int k = 0; k < KT; ++k) {
-          sc[3 * KT + 2 + k] = __dsub_rn(dn[k], sc[k]);   // what the lv phase adds
-          sc[k] = dn[k];
-          sc[2 * KT + k] = (dn[k] - sdc) / sig;
+          for (int q = 1; q < KT; ++q) sd += __shfl_sync(0xffffffffu, dnk, base + q);
+          if (act) {
+            const double sdc = sd / Cd;
+            sc[3 * KT + 2 + uk] = __dsub_rn(dnk, dold);   // what the lv phase adds
+            sc[uk] = dnk;
+            sc[2 * KT + uk] = (dnk - sdc) / sig;
+          }
         }
       }
     }
