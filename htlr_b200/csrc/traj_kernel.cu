@@ -145,9 +145,14 @@ __device__ __forceinline__ long long clk() {
 
 }  // namespace
 
-template <int KT>
+// Columns per tile: at most 8 (column, class) values per tile, and at most 8 double2 of X per thread. With one class and
+// one row pair per thread (K = 1, n <= 64 GW) that can be 8 columns: half as many tiles, i.e. half as many trips through
+// the per-tile barriers and reductions, for the binary problems whose sweeps are bound by those (config D, n = 200:
+// 4520 -> 5480 it/s). Not for one-warp groups (n <= 64: 16 groups per block): with a dozen columns per block the larger
+// tiles keep fewer groups busy (config A: 126 -> 137 us per iteration, measured).
+template <int KT, int NRP, int GW>
 struct TileCols {
-  static constexpr int v = KT <= 2 ? 4 : (KT <= 4 ? 2 : 1);   // (column, class) values per tile: at most 8
+  static constexpr int v = (KT == 1 && NRP == 1 && GW >= 4) ? 8 : (KT <= 2 ? 4 : (KT <= 4 ? 2 : 1));
 };
 
 template <int KT, int NRP, int GW, bool CL>
@@ -155,7 +160,7 @@ __global__ void __launch_bounds__(kFT, 1) k_traj(Geom g, Bufs b, FusedGeom fg, i
   constexpr int NG = kCW / GW;           // compute groups
   constexpr int GT = 32 * GW;            // threads per group
   constexpr int CS = 3 * KT + 2;         // per-column state: d[K], m[K], prior gradient[K], sig, step
-  constexpr int TC = TileCols<KT>::v;    // columns per tile (= ring stage)
+  constexpr int TC = TileCols<KT, NRP, GW>::v;    // columns per tile (= ring stage)
   constexpr int V = TC * KT;             // (column, class) gradient values per tile
   constexpr int VP = V <= 4 ? 4 : 8;     // padded to a power of two for the transposing reduction
   Ctl* ctl = b.ctl;
@@ -900,7 +905,6 @@ bool fused_plan(const Geom& g, int smem_optin_bytes, int cl, FusedGeom* out) {
   // smallest group whose threads keep their row pairs (x, residual, lv partial) in registers
   // row pairs per thread: x (TC x NRP double2), residual and lv partial (4 NRP K doubles) stay in registers
   const int nrp_max = K <= 4 ? 2 : 1;
-  const int TC = K <= 2 ? 4 : (K <= 4 ? 2 : 1);   // TileCols<K>
   int gw = 0;
   const char* force = std::getenv("HTLR_FUSED_GW");   // experiments only
   for (int cand : {1, 4, 8, 16}) {
@@ -909,6 +913,7 @@ bool fused_plan(const Geom& g, int smem_optin_bytes, int cl, FusedGeom* out) {
   }
   if (!gw) return false;
   const int nrp = (npairs + 32 * gw - 1) / (32 * gw);
+  const int TC = (K == 1 && nrp == 1 && gw >= 4) ? 8 : (K <= 2 ? 4 : (K <= 4 ? 2 : 1));   // TileCols<K, NRP, GW>
   const int ng = kCW / gw;
   const size_t col_bytes = (size_t)npairs * 16;
   int ncmax;
