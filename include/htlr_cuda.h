@@ -128,7 +128,7 @@ typedef struct htlr_profile {
   /* fused trajectory kernel, block 0's view (SM cycle counter / clock rate): time in the column sweeps,
    * waiting at the two grid-wide barriers of each leapfrog step, and in the row phase between them */
   double fused_sweep_ms, fused_barrier_ms, fused_rowphase_ms;
-  double small_kernel_trajectories;   /* proposals run by the single-block kernel since create / reset */
+  double small_kernel_trajectories;   /* proposals run by the single-block or the row-partitioned kernel since create / reset */
   /* per-iteration timeline, collected only when the handle was created with HTLR_TIMELINE=1 in the environment
    * (graph replay stays on): microseconds from the start of the previous kernel of the iteration to the start of
    * kernel k, summed over iterations — 0 select (i.e. the tail of the previous iteration), 1 begin, 2 detach
