@@ -525,6 +525,10 @@ def measure_tall(torch, steps, warmup, n_total, dist, rank, world, local, cpu_ba
                     "algorithm": "two-sweep (lv sweep + gradient sweep per leapfrog step)", "mean_nuvar": u,
                     "hmc_reject": float(np.mean(out["mchmcrej"][warmup + 1:warmup + 1 + steps])),
                     "all_ranks_bit_identical": same,
+                    # whether rank 0's GPU can map its peers' memory: NCCL's all-reduce falls back to host shared memory
+                    # when it cannot (43 us per call became 224 us on one 8-GPU lease of round 2)
+                    "peer_access_from_gpu0": [bool(torch.cuda.can_device_access_peer(0, d))
+                                              for d in range(1, torch.cuda.device_count())][:7] if world > 1 else [],
                     "loglike_first_last": [float(np.ravel(out["mcloglike"])[1]), float(np.ravel(out["mcloglike"])[-1])]},
             "gpu_launches": launches, "clocks": clk,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
