@@ -445,6 +445,13 @@ def make_tall_on_device(torch, n_total, p, C, rank, world, seed):
     return dict(Xt=Xt, ld=ld, ymat=ymat, ybase=ybase, n_local=nl, K=C - 1)
 
 
+def _peer_access(torch):
+    try:
+        return [bool(torch.cuda.can_device_access_peer(0, d)) for d in range(1, min(8, torch.cuda.device_count()))]
+    except Exception as e:   # never let a diagnostic break the measurement
+        return [repr(e)[:80]]
+
+
 def measure_tall(torch, steps, warmup, n_total, dist, rank, world, local, cpu_baseline=True):
     """Config E: ONE chain, rows sharded over the ranks, NCCL all-reduce of the gradient partials in every leapfrog
     step. Strong scaling: total work fixed as N grows. Returns the result dict on rank 0, None elsewhere."""
@@ -527,8 +534,7 @@ def measure_tall(torch, steps, warmup, n_total, dist, rank, world, local, cpu_ba
                     "all_ranks_bit_identical": same,
                     # whether rank 0's GPU can map its peers' memory: NCCL's all-reduce falls back to host shared memory
                     # when it cannot (43 us per call became 224 us on one 8-GPU lease of round 2)
-                    "peer_access_from_gpu0": [bool(torch.cuda.can_device_access_peer(0, d))
-                                              for d in range(1, torch.cuda.device_count())][:7] if world > 1 else [],
+                    "peer_access_from_gpu0": _peer_access(torch) if world > 1 else [],
                     "loglike_first_last": [float(np.ravel(out["mcloglike"])[1]), float(np.ravel(out["mcloglike"])[-1])]},
             "gpu_launches": launches, "clocks": clk,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
