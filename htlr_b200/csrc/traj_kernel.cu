@@ -31,18 +31,19 @@
 //   smallest group that keeps a thread's row pairs in registers.
 // After each sweep the group partials are summed in shared memory, the per-block lv partials are summed in
 // block order (deterministic) and added to the rows' running lv, rows are soft-maxed (K >= 3: one lane per class)
-// and the new residual is published: two grid-wide barriers per leapfrog step. The log-likelihood is reduced once,
-// after the last step.
+// and the new residual is published: two grid-wide barriers per leapfrog step in grid mode. The log-likelihood is
+// reduced once, after the last step.
 //
 // Two flavours (template flag CL):
 //   grid mode    — one block per SM, cooperative launch; partials and residual travel through L2 and the two
 //                  barriers per step are release/acquire counters in global memory (~1.2 us each). Right when
 //                  the restricted set is large (HBM-bound).
-//   cluster mode — ONE thread-block cluster (16 CTAs, or 8); each block's lv partial stays in its own shared
-//                  memory and is read by the row owners through distributed shared memory, the new residual is
-//                  pushed into every block's shared memory, and the two barriers per step are hardware cluster
-//                  barriers. Right for small restricted sets (the product default, cut = 0.05), where a
-//                  leapfrog step is pure latency.
+//   cluster mode — ONE thread-block cluster (16 CTAs, or 8), everything through distributed shared memory and no
+//                  barrier inside the trajectory: a block pushes its lv partial to the owners of the rows and the
+//                  owners push the new residual to every block as st.async stores that count themselves in on
+//                  a transaction barrier of the receiver (a cluster barrier's release is a MEMBAR.ALL.GPU: an L2
+//                  round trip for data that never leaves shared memory). Right for small restricted sets (the
+//                  product default, cut = 0.05), where a leapfrog step is pure latency.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
