@@ -690,7 +690,7 @@ void do_create(const htlr_cfg* cfg, const double* X, int64_t ldx, const double* 
                    (((c.algo == HTLR_ALGO_AUTO || c.algo == HTLR_ALGO_CLUSTER_ONLY) && g.n <= 256) ||
                     c.algo == HTLR_ALGO_SMALL_FIRST);
     // Row-partitioned kernel: largest restricted set (columns) it is handed, from tools/rows_sweep.py (us per iteration
-    // against k_traj's cluster mode over n = 300..2000, K = 1..4, u = 4..128, profiles/r02_exchange/rows_sweep.jsonl;
+    // against k_traj's cluster mode over n = 300..2000, K = 1..4, u = 4..128, profiles/r02_rules/rows_sweep.jsonl;
     // e.g. n = 1000 / K = 4 / u = 8: 185 vs 338, n = 500 / K = 3 / u = 12: 164 vs 208, n = 1000 / K = 2 / u = 32: 187 vs 201,
     // n = 500 / K = 1: never). Rows: K = 1..4; columns: n < 800, n < 1500, n >= 1500.
     static const int kRowsUMax[4][3] = {{0, 16, 32}, {32, 32, 32}, {24, 32, 64}, {32, 64, 64}};
